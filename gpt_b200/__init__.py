@@ -1,0 +1,21 @@
+"""
+gpt_b200 -- B200-native drop-in for the fermion-operator hot path of GPT (lehner/gpt).
+
+Usage mirrors the reference (`import gpt as g`):  import gpt_b200 as g
+The arithmetic lives in gpt_b200/lib/libcgpt_b200.so (CUDA, sm_100a) behind the C ABI of include/cgpt_b200.h.
+"""
+from gpt_b200 import cgpt
+from gpt_b200.params import params_convention
+from gpt_b200.core import *  # noqa: F401,F403
+from gpt_b200.core import eval, slice, time, complex  # noqa: F401,A004  (GPT's names shadow builtins on purpose)
+from gpt_b200 import algorithms, qcd
+import sys as _sys
+
+
+class _callable_module(_sys.modules[__name__].__class__):
+    # g(expr) == g.eval(expr)   (lib/gpt/__init__.py)
+    def __call__(self, first, second=None, ac=False):
+        return eval(first, second, ac)
+
+
+_sys.modules[__name__].__class__ = _callable_module

@@ -1,0 +1,688 @@
+"""
+Host-side mirror of the slice of GPT's core objects that the fermion-operator hot path touches: precision,
+grid, lattice, lazy linear expressions, matrix_operator and the vector transforms.  Names, argument meaning
+and error behaviour follow the reference (file:line relative to /root/reference):
+
+  precision        lib/gpt/core/precision.py
+  grid             lib/gpt/core/grid.py:31-37,96-271
+  lattice          lib/gpt/core/lattice.py:57-122,301-303
+  expr / eval      lib/gpt/core/expr.py:126-143,316-412
+  matrix_operator  lib/gpt/core/operator/matrix_operator.py:35-305
+  transforms       lib/gpt/core/transform.py:101-153, core/checkerboard.py:56-81, core/basis.py:66-74
+
+All arithmetic happens in libcgpt_b200.so through gpt_b200.cgpt; this file holds no numerics.
+"""
+import builtins
+import numbers
+import sys
+import time as _time
+
+import numpy as np
+
+from gpt_b200 import cgpt
+
+
+# ---- precision -----------------------------------------------------------------------------------------
+class _precision:
+    def __init__(self, name, real, cplx, nbytes, eps, code):
+        self.__name__ = name
+        self.cgpt_dtype = name
+        self.real_dtype = real
+        self.complex_dtype = cplx
+        self.nbytes = nbytes
+        self.eps = eps
+        self.code = code
+
+    def __repr__(self):
+        return self.__name__
+
+
+single = _precision("single", np.float32, np.complex64, 4, 1e-7, cgpt.SINGLE)
+double = _precision("double", np.float64, np.complex128, 8, 1e-15, cgpt.DOUBLE)
+
+
+# ---- checkerboards ---------------------------------------------------------------------------------------
+class _cb:
+    def __init__(self, name, tag):
+        self.__name__ = name
+        self.tag = tag
+
+    def inv(self):
+        return {cgpt.EVEN: odd, cgpt.ODD: even, cgpt.FULL: none}[self.tag]
+
+    def __repr__(self):
+        return self.__name__
+
+
+even = _cb("even", cgpt.EVEN)
+odd = _cb("odd", cgpt.ODD)
+none = _cb("none", cgpt.FULL)
+_cb_of = {cgpt.EVEN: even, cgpt.ODD: odd, cgpt.FULL: none}
+
+
+class full:
+    n = 1
+    __name__ = "full"
+
+
+class redblack:
+    n = 2
+    __name__ = "redblack"
+
+
+# ---- grid --------------------------------------------------------------------------------------------------
+class grid:
+    """g.grid(fdimensions, precision, cb=full): 4d [x,y,z,t] or 5d [s,x,y,z,t] (s never checkerboarded)."""
+
+    def __init__(self, fdimensions, precision, cb=None, parent=None, mpi=None):
+        self.fdimensions = [int(x) for x in fdimensions]
+        self.gdimensions = list(self.fdimensions)
+        self.ldimensions = list(self.fdimensions)
+        self.nd = len(self.fdimensions)
+        if self.nd not in (4, 5):
+            raise ValueError("only 4d and 5d grids are supported")
+        self.precision = precision
+        self.cb = full if cb is None else cb
+        self.parent = parent
+        self.mpi = mpi if mpi is not None else [1] * self.nd
+        self.processor = 0
+        self.Nprocessors = 1
+        self.gsites = int(np.prod(self.fdimensions))
+        self.obj = self  # cgpt grid handles are not needed: a lattice carries its geometry
+
+    @property
+    def dims4(self):
+        return self.fdimensions[-4:]
+
+    @property
+    def Ls(self):
+        return self.fdimensions[0] if self.nd == 5 else 0
+
+    def checkerboarded(self, cb):
+        return grid(self.fdimensions, self.precision, cb)
+
+    def converted(self, precision):
+        return grid(self.fdimensions, precision, self.cb)
+
+    def inserted_dimension(self, dimension, extent, cb_mask=None):
+        assert dimension == 0 and self.nd == 4
+        return grid([extent] + self.fdimensions, self.precision, self.cb)
+
+    def removed_dimension(self, dimension):
+        assert dimension == 0 and self.nd == 5
+        return grid(self.fdimensions[1:], self.precision, self.cb)
+
+    def __eq__(self, other):
+        return (
+            isinstance(other, grid)
+            and self.fdimensions == other.fdimensions
+            and self.precision is other.precision
+            and self.cb.n == other.cb.n
+        )
+
+    def __hash__(self):
+        return hash((tuple(self.fdimensions), self.precision.__name__, self.cb.n))
+
+    def __str__(self):
+        return f"{self.fdimensions};{self.precision.__name__};{self.cb.__name__}"
+
+    def barrier(self):
+        cgpt.accelerator_barrier()
+
+    def globalsum(self, x):
+        return x
+
+
+# ---- object types ----------------------------------------------------------------------------------------------
+class _otype:
+    def __init__(self, name, shape, code):
+        self.__name__ = name
+        self.shape = shape
+        self.nfloats = 2 * int(np.prod(shape)) if shape else 2
+        self.code = code
+        if name == "ot_matrix_su_n_fundamental_group(3)":
+            self.Nc = 3
+
+    def __repr__(self):
+        return self.__name__
+
+
+ot_singlet = _otype("ot_singlet", (), cgpt.OT_SINGLET)
+ot_matrix_su_n_fundamental_group_3 = _otype("ot_matrix_su_n_fundamental_group(3)", (3, 3), cgpt.OT_MCOLOR)
+ot_vector_spin_color_4_3 = _otype("ot_vector_spin_color(4,3)", (4, 3), cgpt.OT_VSPINCOLOR)
+
+
+def ot_vector_spin_color(ns, nc):
+    assert (ns, nc) == (4, 3)
+    return ot_vector_spin_color_4_3
+
+
+def ot_matrix_su_n_fundamental_group(nc):
+    assert nc == 3
+    return ot_matrix_su_n_fundamental_group_3
+
+
+# ---- lattice -----------------------------------------------------------------------------------------------------
+class lattice:
+    """g.lattice(grid, otype) or g.lattice(other) (same grid/otype/checkerboard, uninitialised)."""
+
+    def __init__(self, first, otype=None, device_ptr=None):
+        if isinstance(first, lattice):
+            self.grid = first.grid
+            self.otype = first.otype
+            cb = first.checkerboard().tag
+        else:
+            self.grid = first
+            self.otype = otype
+            cb = cgpt.FULL if first.cb.n == 1 else cgpt.EVEN
+        g = self.grid
+        self.obj = cgpt.create_lattice(g.dims4, g.Ls, g.precision.code, self.otype.code, cb, device_ptr)
+        self.v_obj = [self.obj]
+
+    def __del__(self):
+        if getattr(self, "obj", None) is not None:
+            cgpt.delete_lattice(self.obj)
+            self.obj = None
+
+    # -- checkerboard label
+    def checkerboard(self, val=None):
+        if val is None:
+            return _cb_of[cgpt.lattice_get_checkerboard(self.obj)]
+        if val is not none:
+            assert self.grid.cb.n != 1
+            cgpt.lattice_change_checkerboard(self.obj, val.tag)
+        return self
+
+    # -- host views in GPT order
+    def _host_shape(self):
+        return (int(cgpt.lattice_bytes(self.obj) // (self.otype.nfloats * self.grid.precision.nbytes)),) + tuple(
+            self.otype.shape
+        )
+
+    def __getitem__(self, key):
+        a = np.empty(self._host_shape(), dtype=self.grid.precision.complex_dtype)
+        cgpt.lattice_export(self.obj, a)
+        if isinstance(key, slice) and key == slice(None):
+            return a
+        if isinstance(key, tuple) and len(key) == self.grid.nd and all(isinstance(k, (int, np.integer)) for k in key):
+            assert self.grid.cb.n == 1
+            idx = 0
+            for d in reversed(range(self.grid.nd)):
+                idx = idx * self.grid.fdimensions[d] + int(key[d])
+            return a[idx]
+        raise NotImplementedError("lattice[...] supports [:] and full-lattice point access")
+
+    def __setitem__(self, key, value):
+        if isinstance(key, slice) and key == slice(None):
+            if isinstance(value, numbers.Number) and value == 0:
+                cgpt.lattice_set_to_zero(self.obj)
+                return
+            a = np.asarray(value)
+            if a.shape != self._host_shape() and a.size != int(np.prod(self._host_shape())):
+                raise ValueError(f"shape mismatch: {a.shape} vs {self._host_shape()}")
+            cgpt.lattice_import(self.obj, np.ascontiguousarray(a, dtype=self.grid.precision.complex_dtype))
+            return
+        if isinstance(key, tuple) and len(key) == self.grid.nd:
+            a = self[:]
+            idx = 0
+            for d in reversed(range(self.grid.nd)):
+                idx = idx * self.grid.fdimensions[d] + int(key[d])
+            a[idx] = np.asarray(value, dtype=a.dtype).reshape(a[idx].shape)
+            cgpt.lattice_import(self.obj, a)
+            return
+        raise NotImplementedError("lattice[...] = supports [:] and full-lattice point access")
+
+    # -- expression sugar
+    def __mul__(self, other):
+        return expr(self) * other
+
+    def __rmul__(self, other):
+        return other * expr(self)
+
+    def __add__(self, other):
+        return expr(self) + other
+
+    def __sub__(self, other):
+        return expr(self) - other
+
+    def __neg__(self):
+        return -1.0 * expr(self)
+
+    def __truediv__(self, other):
+        return expr(self) * (1.0 / other)
+
+    def __imatmul__(self, other):
+        eval(self, other)
+        return self
+
+    def __iadd__(self, other):
+        eval(self, other, ac=True)
+        return self
+
+    def __isub__(self, other):
+        eval(self, -1.0 * expr(other), ac=True)
+        return self
+
+    def __imul__(self, other):
+        cgpt.lattice_scale(self.obj, other)
+        return self
+
+    def __itruediv__(self, other):
+        cgpt.lattice_scale(self.obj, 1.0 / other)
+        return self
+
+    def global_bytes(self):
+        return int(cgpt.lattice_bytes(self.obj))
+
+
+def vspincolor(grid_):
+    return lattice(grid_, ot_vector_spin_color_4_3)
+
+
+def mcolor(grid_):
+    return lattice(grid_, ot_matrix_su_n_fundamental_group_3)
+
+
+def complex(grid_):  # noqa: A001  (GPT's name)
+    return lattice(grid_, ot_singlet)
+
+
+# ---- expressions ---------------------------------------------------------------------------------------------------
+class expr:
+    """
+    Lazy linear combination  sum_i c_i * (op_i1 * op_i2 * ... * lattice_i), evaluated right-to-left like
+    lib/gpt/core/expr.py:316-330; every operator factor allocates its result from its vector space.
+    """
+
+    def __init__(self, first=None, terms=None):
+        if terms is not None:
+            self.terms = terms
+        elif isinstance(first, expr):
+            self.terms = list(first.terms)
+        elif isinstance(first, lattice):
+            self.terms = [(1.0, [first])]
+        elif isinstance(first, matrix_operator):
+            self.terms = [(1.0, [first])]
+        elif first is None:
+            self.terms = []
+        else:
+            raise TypeError(f"cannot build an expression from {type(first)}")
+
+    def __mul__(self, other):
+        if isinstance(other, numbers.Number):
+            return expr(terms=[(c * other, f) for c, f in self.terms])
+        other = expr(other)
+        return expr(terms=[(c1 * c2, f1 + f2) for c1, f1 in self.terms for c2, f2 in other.terms])
+
+    def __rmul__(self, other):
+        if isinstance(other, numbers.Number):
+            return expr(terms=[(c * other, f) for c, f in self.terms])
+        return expr(other) * self
+
+    def __add__(self, other):
+        return expr(terms=self.terms + expr(other).terms)
+
+    def __sub__(self, other):
+        return expr(terms=self.terms + [(-c, f) for c, f in expr(other).terms])
+
+    def __neg__(self):
+        return expr(terms=[(-c, f) for c, f in self.terms])
+
+    def __truediv__(self, other):
+        return self * (1.0 / other)
+
+
+def _apply_chain(factors):
+    cur = factors[-1]
+    if not isinstance(cur, lattice):
+        raise TypeError("right-most factor of a product must be a lattice")
+    for op in reversed(factors[:-1]):
+        if not isinstance(op, matrix_operator):
+            raise TypeError("factors left of a lattice must be matrix operators")
+        cur = op(cur)
+    return cur
+
+
+def eval(first, second=None, ac=False):  # noqa: A001  (GPT's name)
+    """g.eval(expr) -> new lattice ; g.eval(dst, expr[, ac]) -> dst (+)= expr   (expr.py:333-412)"""
+    if second is None:
+        e, dst = first, None
+        if isinstance(e, (lattice, mspincolor)):
+            return e
+        if isinstance(e, _deferred):
+            return e.op(e.arg)
+    else:
+        dst, e = first, second
+    e = expr(e)
+    vals = [(c, _apply_chain(f)) for c, f in e.terms]
+    if dst is None:
+        dst = lattice(vals[0][1])
+    cgpt.lattice_lc(dst.obj, ac, [c for c, _ in vals], [v.obj for _, v in vals])
+    return dst
+
+
+# ---- matrix_operator -------------------------------------------------------------------------------------------------
+class vector_space:
+    """where the result of an operator lives (lib/gpt/core/vector_space.py, explicit_grid_otype)"""
+
+    def __init__(self, grid_, otype, cb=None):
+        self.grid = grid_
+        self.otype = otype
+        self.cb = cb
+
+    def lattice(self):
+        l = lattice(self.grid, self.otype)
+        if self.cb is not None and self.grid.cb.n != 1:
+            l.checkerboard(self.cb)
+        return l
+
+    def clone(self):
+        return vector_space(self.grid, self.otype, self.cb)
+
+    def converted(self, precision):
+        return vector_space(self.grid.converted(precision), self.otype, self.cb)
+
+
+class matrix_operator:
+    def __init__(self, mat, adj_mat=None, inv_mat=None, adj_inv_mat=None, vector_space=None,
+                 accept_guess=(False, False), accept_list=False):
+        self.mat = mat
+        self.adj_mat = adj_mat
+        self.inv_mat = inv_mat
+        self.adj_inv_mat = adj_inv_mat
+        self.vector_space = vector_space if isinstance(vector_space, tuple) else (vector_space, vector_space)
+        self.accept_guess = accept_guess if isinstance(accept_guess, tuple) else (accept_guess, accept_guess)
+        self.accept_list = accept_list
+
+    def inv(self):
+        return matrix_operator(self.inv_mat, self.adj_inv_mat, self.mat, self.adj_mat,
+                               tuple(reversed(self.vector_space)), tuple(reversed(self.accept_guess)), self.accept_list)
+
+    def adj(self):
+        return matrix_operator(self.adj_mat, self.mat, self.adj_inv_mat, self.inv_mat,
+                               tuple(reversed(self.vector_space)), tuple(reversed(self.accept_guess)), self.accept_list)
+
+    def clone(self):
+        vs = tuple(v.clone() if v is not None else None for v in self.vector_space)
+        return matrix_operator(self.mat, self.adj_mat, self.inv_mat, self.adj_inv_mat, vs, self.accept_guess,
+                               self.accept_list)
+
+    def specialized_singlet_callable(self):
+        return self.mat if not self.accept_list else self
+
+    def __mul__(self, other):
+        if isinstance(other, matrix_operator):
+            return matrix_operator_product([self, other])
+        return expr(self) * expr(other)
+
+    def __rmul__(self, other):
+        return expr(self) * other
+
+    def _new_dst(self, src):
+        vs = self.vector_space[0]
+        if vs is None:
+            dst = lattice(src)
+        else:
+            dst = vs.lattice()
+            if vs.cb is None and dst.grid.cb.n != 1 and src.grid.cb.n != 1:
+                dst.checkerboard(src.checkerboard())
+        if self.accept_guess[0]:
+            dst[:] = 0
+        return dst
+
+    def __call__(self, first, second=None):
+        """op(src) -> new dst ; op(dst, src) -> dst    (matrix_operator.py:256-305)"""
+        if self.mat is None:
+            raise NotImplementedError("matrix_operator has no matrix defined for this direction")
+        if second is None:
+            src = first
+            if isinstance(src, expr):
+                src = eval(src)
+            if isinstance(src, list):
+                dst = [self._new_dst(s) for s in src]
+            else:
+                dst = self._new_dst(src)
+        else:
+            dst, src = first, second
+        if isinstance(src, list):
+            if self.accept_list:
+                self.mat(dst, src)
+            else:
+                for d, s in zip(dst, src):
+                    self.mat(d, s)
+        else:
+            if self.accept_list:
+                self.mat([dst], [src])
+            else:
+                self.mat(dst, src)
+        return dst
+
+
+class matrix_operator_product(matrix_operator):
+    def __init__(self, factors):
+        self.factors = factors
+
+        def _mat(dst, src):
+            cur = src
+            for f in reversed(factors[1:]):
+                cur = f(cur)
+            factors[0](dst, cur)
+
+        super().__init__(_mat, vector_space=(factors[0].vector_space[0], factors[-1].vector_space[1]),
+                         accept_guess=(factors[0].accept_guess[0], factors[-1].accept_guess[1]))
+
+    def adj(self):
+        return matrix_operator_product([f.adj() for f in reversed(self.factors)])
+
+    def inv(self):
+        return matrix_operator_product([f.inv() for f in reversed(self.factors)])
+
+    def __mul__(self, other):
+        if isinstance(other, matrix_operator_product):
+            return matrix_operator_product(self.factors + other.factors)
+        if isinstance(other, matrix_operator):
+            return matrix_operator_product(self.factors + [other])
+        return expr(self) * expr(other)
+
+
+# ---- transforms ------------------------------------------------------------------------------------------------------
+def copy(first, second=None):
+    if second is None:
+        dst = lattice(first)
+        cgpt.copy(dst.obj, first.obj)
+        return dst
+    cgpt.copy(first.obj, second.obj)
+    return first
+
+
+def convert(first, second):
+    """g.convert(dst, src) or g.convert(src, precision) (also for lists)"""
+    if isinstance(first, list):
+        return [convert(x, second) for x in first]
+    if isinstance(second, _precision):
+        src = first
+        dst = lattice(src.grid.converted(second), src.otype)
+        cgpt.convert(dst.obj, src.obj)
+        return dst
+    cgpt.convert(first.obj, second.obj)
+    return first
+
+
+def norm2(l):
+    if isinstance(l, list):
+        return [norm2(x) for x in l]
+    l = eval(l)
+    return cgpt.lattice_norm2(l.obj)
+
+
+def inner_product(a, b):
+    a, b = eval(a), eval(b)
+    return builtins.complex(cgpt.lattice_rank_inner_product([a.obj], [b.obj])[0, 0])
+
+
+def rank_inner_product(a, b, use_accelerator=True):
+    return inner_product(a, b)
+
+
+def inner_product_norm2(a, b):
+    return cgpt.lattice_inner_product_norm2(a.obj, b.obj)
+
+
+def axpy(d, a, x, y):
+    cgpt.lattice_axpy(d.obj, a, x.obj, y.obj)
+
+
+def axpy_norm2(d, a, x, y):
+    return cgpt.lattice_axpy_norm2(d.obj, a, x.obj, y.obj)
+
+
+def linear_combination(r, basis, Qt, n_block=8):
+    rr = r if isinstance(r, list) else [r]
+    q = np.atleast_2d(np.asarray(Qt))
+    cgpt.linear_combination([x.obj for x in rr], [b.obj for b in basis], q)
+    return r
+
+
+def pick_checkerboard(cb, dst, src):
+    cgpt.lattice_pick_checkerboard(cb.tag, dst.obj, src.obj)
+    return dst
+
+
+def set_checkerboard(dst, src):
+    cgpt.lattice_set_checkerboard(dst.obj, src.obj)
+    return dst
+
+
+# ---- logging / timing ------------------------------------------------------------------------------------------------
+_t0 = _time.time()
+
+
+def time():  # noqa: A001
+    return _time.time() - _t0
+
+
+def message(*a):
+    import os
+
+    if int(os.environ.get("RANK", "0")) == 0:
+        print("GPT_B200 : %14.6f s :" % time(), *a)
+        sys.stdout.flush()
+
+
+# ---- spin-colour matrix fields (propagators) as 12 spin-colour vector columns ----------------------------------------
+class mspincolor:
+    """
+    g.mspincolor(grid): a 12x12 spin-colour matrix field held as its 12 columns (spin-colour vectors) -- the
+    decomposition GPT applies before a solver sees a propagator source
+    (lib/gpt/core/object_type/container.py:330-357, core/operator/matrix_operator.py:290-295).
+    """
+
+    def __init__(self, grid_):
+        self.grid = grid_
+        self.columns = [vspincolor(grid_) for _ in range(12)]
+        for c in self.columns:
+            c[:] = 0
+
+    def __getitem__(self, key):
+        if isinstance(key, slice) and key == slice(None):
+            # [site, spin_i, spin_j, color_a, color_b] like GPT's mspincolor tensor
+            cols = np.stack([c[:] for c in self.columns], axis=-1)  # [site, 4, 3, 12]
+            n = cols.shape[0]
+            return cols.reshape(n, 4, 3, 4, 3).transpose(0, 1, 3, 2, 4)
+        raise NotImplementedError
+
+    def __mul__(self, other):
+        if isinstance(other, _adjoint) and isinstance(other.x, mspincolor):
+            return _ab_dagger(self, other.x)
+        return NotImplemented
+
+
+class _adjoint:
+    def __init__(self, x):
+        self.x = x
+
+
+class _ab_dagger:
+    def __init__(self, a, b):
+        self.a, self.b = a, b
+
+
+class _trace_ab_dagger:
+    def __init__(self, a, b):
+        self.a, self.b = a, b
+
+
+def adj(x):
+    if isinstance(x, matrix_operator):
+        return x.adj()
+    return _adjoint(x)
+
+
+def inv(x):
+    return x.inv()
+
+
+def trace(x):
+    if isinstance(x, _ab_dagger):
+        return _trace_ab_dagger(x.a, x.b)
+    raise NotImplementedError("g.trace is implemented for prop * g.adj(prop)")
+
+
+def slice(x, dim):  # noqa: A001  (GPT's name)
+    """g.slice(g.trace(a * g.adj(b)), 3) -> list of complex per time slice (lib/gpt/core/transform.py:170-171)"""
+    if isinstance(x, _trace_ab_dagger) and dim == 3:
+        nt = x.a.grid.fdimensions[-1]
+        acc = np.zeros(nt, dtype=np.complex128)
+        for ca, cb_ in zip(x.a.columns, x.b.columns):
+            acc += cgpt.lattice_slice_inner_product(cb_.obj, ca.obj, nt)
+        return [builtins.complex(v) for v in acc]
+    raise NotImplementedError("g.slice is implemented for g.trace(a * g.adj(b)) along time")
+
+
+class _create:
+    @staticmethod
+    def point(src, pos):
+        """g.create.point(src, pos): unit spin-colour matrix at `pos`, zero elsewhere (lib/gpt/create/point.py)"""
+        assert isinstance(src, mspincolor)
+        gr = src.grid
+        idx = 0
+        for d in reversed(range(gr.nd)):
+            idx = idx * gr.fdimensions[d] + int(pos[d])
+        for j, col in enumerate(src.columns):
+            a = np.zeros((gr.gsites, 4, 3), dtype=gr.precision.complex_dtype)
+            a.reshape(gr.gsites, 12)[idx, j] = 1.0
+            col[:] = a
+        return src
+
+
+create = _create()
+
+
+class propagator_operator(matrix_operator):
+    """a spin-colour-vector operator that also accepts mspincolor sources column by column"""
+
+    def __init__(self, op):
+        self.op = op
+        super().__init__(op.mat, op.adj_mat, op.inv_mat, op.adj_inv_mat, op.vector_space, op.accept_guess, op.accept_list)
+
+    def __call__(self, first, second=None):
+        src = first if second is None else second
+        if isinstance(src, mspincolor):
+            dst = mspincolor(self.vector_space[0].grid) if second is None else first
+            for d, s in zip(dst.columns, src.columns):
+                matrix_operator.__call__(self, d, s)
+            return dst
+        return matrix_operator.__call__(self, first, second)
+
+    def __mul__(self, other):
+        if isinstance(other, mspincolor):
+            return _deferred(self, other)
+        return matrix_operator.__mul__(self, other)
+
+    def adj(self):
+        return propagator_operator(self.op.adj())
+
+
+class _deferred:
+    def __init__(self, op, arg):
+        self.op, self.arg = op, arg

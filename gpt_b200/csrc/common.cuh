@@ -1,0 +1,212 @@
+// Shared declarations of libcgpt_b200: lattice object, HBM layout accessors, error handling.
+//
+// HBM layout (DESIGN.md "Data layout"):
+//   * a full-lattice field is stored as [even half][odd half]; a checkerboarded field is one half.
+//     Within a half the 4d sites are in checkerboard order i4 = (x/2) + Lx/2*(y + Ly*(z + Lz*t)); a 5d
+//     field has the s index fastest: site = i4*Ls + s (Grid's order, evidence:
+//     lib/cgpt/lib/foundation/mobius_with_vector_field.h:79-81).
+//   * site-major SoA in 16-byte vector blocks: element block k of site i lives at data16[k*nsites + i].
+//     fp64: one complex per block (12 blocks per spinor); fp32 spinor: two complex per block (6 blocks);
+//     other fp32 objects (links, singlets): one complex (8 bytes) per block.
+//     A warp reading block k of 32 consecutive sites issues one fully coalesced 512-byte request.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/cgpt_b200.h"
+
+namespace cgptb {
+
+extern thread_local std::string g_error;
+extern cudaStream_t g_stream;
+extern uint64_t g_launches;
+
+struct Error {
+  std::string msg;
+};
+
+#define CGPTB_ERR(...)                                   \
+  do {                                                   \
+    char _buf[1024];                                     \
+    snprintf(_buf, sizeof(_buf), __VA_ARGS__);           \
+    throw cgptb::Error{std::string(_buf)};               \
+  } while (0)
+
+#define CGPTB_ASSERT(x)                                                              \
+  do {                                                                               \
+    if (!(x)) CGPTB_ERR("Assert failed: %s (%s:%d)", #x, __FILE__, __LINE__);        \
+  } while (0)
+
+#define CUDA_CHECK(x)                                                                                  \
+  do {                                                                                                 \
+    cudaError_t _e = (x);                                                                              \
+    if (_e != cudaSuccess) CGPTB_ERR("CUDA error %s at %s:%d", cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// wrap every C-ABI body: exceptions become a status code + message (cgpt: exception.h:23-39)
+#define CGPTB_API_BEGIN try {
+#define CGPTB_API_END                                    \
+  }                                                      \
+  catch (const cgptb::Error& e) {                        \
+    cgptb::g_error = e.msg;                              \
+    fprintf(stderr, "cgpt_b200: %s\n", e.msg.c_str());   \
+    return 1;                                            \
+  }                                                      \
+  return 0;
+
+#define LAUNCH_CHECK()              \
+  do {                              \
+    cgptb::g_launches++;            \
+    CUDA_CHECK(cudaGetLastError()); \
+  } while (0)
+
+}  // namespace cgptb
+
+struct cgptb_lattice {
+  int prec;     // CGPTB_SINGLE / CGPTB_DOUBLE
+  int otype;    // complex components per site
+  int dims4[4];
+  int Ls;       // 0: 4d
+  int cb;       // CGPTB_EVEN / ODD / FULL
+  size_t sites4;  // stored 4d sites (V4 or V4/2)
+  size_t sites;   // stored sites (sites4 * max(Ls,1))
+  void* data;
+  bool owns;
+
+  int ls() const { return Ls > 0 ? Ls : 1; }
+  size_t real_size() const { return prec == CGPTB_DOUBLE ? 8 : 4; }
+  size_t nreals() const { return sites * (size_t)otype * 2; }
+  size_t bytes() const { return nreals() * real_size(); }
+  size_t half4() const { return (size_t)dims4[0] * dims4[1] * dims4[2] * dims4[3] / 2; }
+  // complex components per 16-byte (or 8-byte) block
+  int cpb() const { return (prec == CGPTB_SINGLE && otype % 2 == 0) ? 2 : 1; }
+};
+
+namespace cgptb {
+
+inline bool same_shape(const cgptb_lattice* a, const cgptb_lattice* b) {
+  return a->prec == b->prec && a->otype == b->otype && a->Ls == b->Ls && a->sites == b->sites &&
+         a->dims4[0] == b->dims4[0] && a->dims4[1] == b->dims4[1] && a->dims4[2] == b->dims4[2] &&
+         a->dims4[3] == b->dims4[3];
+}
+
+template <typename T>
+struct vec_of;
+template <>
+struct vec_of<float> {
+  typedef float4 type;
+};
+template <>
+struct vec_of<double> {
+  typedef double2 type;
+};
+
+// ---- spinor accessors (24 reals: index (spin*3+color)*2 + reim) -----------------------------------
+__device__ __forceinline__ void load_spinor(const float* __restrict__ base, size_t nsites, size_t site, float (&p)[24]) {
+  const float4* b = reinterpret_cast<const float4*>(base);
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    float4 v = __ldg(b + k * nsites + site);
+    p[4 * k + 0] = v.x;
+    p[4 * k + 1] = v.y;
+    p[4 * k + 2] = v.z;
+    p[4 * k + 3] = v.w;
+  }
+}
+__device__ __forceinline__ void load_spinor(const double* __restrict__ base, size_t nsites, size_t site, double (&p)[24]) {
+  const double2* b = reinterpret_cast<const double2*>(base);
+#pragma unroll
+  for (int k = 0; k < 12; k++) {
+    double2 v = __ldg(b + k * nsites + site);
+    p[2 * k + 0] = v.x;
+    p[2 * k + 1] = v.y;
+  }
+}
+__device__ __forceinline__ void store_spinor(float* __restrict__ base, size_t nsites, size_t site, const float (&p)[24]) {
+  float4* b = reinterpret_cast<float4*>(base);
+#pragma unroll
+  for (int k = 0; k < 6; k++) b[k * nsites + site] = make_float4(p[4 * k], p[4 * k + 1], p[4 * k + 2], p[4 * k + 3]);
+}
+__device__ __forceinline__ void store_spinor(double* __restrict__ base, size_t nsites, size_t site, const double (&p)[24]) {
+  double2* b = reinterpret_cast<double2*>(base);
+#pragma unroll
+  for (int k = 0; k < 12; k++) b[k * nsites + site] = make_double2(p[2 * k], p[2 * k + 1]);
+}
+
+// generic complex-element accessor for any object type (used by import/export and setup kernels)
+template <typename T>
+__device__ __forceinline__ size_t elem_offset(size_t nsites, size_t site, int c, int cpb) {
+  // offset in units of T of the real part of complex component c of `site`
+  return ((size_t)(c / cpb) * nsites + site) * (2 * cpb) + (size_t)(c % cpb) * 2;
+}
+
+// geometry of one parity of the local 4d lattice
+struct Geom {
+  int L[4];    // x,y,z,t
+  int hx;      // L[0]/2
+  int half4;   // sites per parity
+};
+
+inline Geom make_geom(const int dims4[4]) {
+  Geom g;
+  for (int i = 0; i < 4; i++) g.L[i] = dims4[i];
+  g.hx = dims4[0] / 2;
+  g.half4 = dims4[0] / 2 * dims4[1] * dims4[2] * dims4[3];
+  return g;
+}
+
+__host__ __device__ __forceinline__ void cb_coords(const Geom& g, int p, int i, int& x, int& y, int& z, int& t) {
+  int xh = i % g.hx;
+  int r = i / g.hx;
+  y = r % g.L[1];
+  r /= g.L[1];
+  z = r % g.L[2];
+  t = r / g.L[2];
+  x = 2 * xh + ((y + z + t + p) & 1);
+}
+
+__host__ __device__ __forceinline__ int cb_index(const Geom& g, int x, int y, int z, int t) {
+  return (x >> 1) + g.hx * (y + g.L[1] * (z + g.L[2] * t));
+}
+
+// warp + block reduction of doubles (n values per thread), result valid in thread 0
+template <int N>
+__device__ __forceinline__ void block_reduce(double (&v)[N], double* smem /* [32*N] */) {
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  }
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < N; i++) smem[w * N + i] = v[i];
+  }
+  __syncthreads();
+  if (w == 0) {
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      double x = lane < nw ? smem[lane * N + i] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      v[i] = x;
+    }
+  }
+}
+
+// scratch for reductions
+double* reduce_scratch(size_t n_doubles);  // device
+double* reduce_host(size_t n_doubles);     // pinned host
+int sm_count();
+
+// internal entry points shared between translation units
+void blas_axpy(cgptb_lattice* r, double are, double aim, const cgptb_lattice* x, const cgptb_lattice* y);
+void blas_copy(cgptb_lattice* d, const cgptb_lattice* s);
+void blas_zero(cgptb_lattice* d);
+void blas_lc(cgptb_lattice* dst, int accumulate, int n, const double* coef, const cgptb_lattice* const* a);
+
+}  // namespace cgptb

@@ -1,0 +1,45 @@
+// Fermion operator object of libcgpt_b200 (the thing a cgpt fermion-operator handle points to,
+// lib/cgpt/lib/operators/base.h, implementation.h:47-110).
+#pragma once
+#include <math.h>
+#include "common.cuh"
+
+namespace cgptb {
+struct LinkCoef {
+  double w[4];    // -c_mu / 2
+  double ph[8];   // boundary phases (re,im)
+  int goff[4];    // global offset of the local lattice (multi-GPU decomposition)
+  int gL[4];      // global extents
+};
+}  // namespace cgptb
+
+struct cgptb_fermion_operator {
+  int type = 0, prec = 0;
+  int dims4[4] = {0, 0, 0, 0};
+  int Ls = 0;
+  cgptb::Geom g;
+  cgptb_fermion_params p;
+  void* links[2] = {0, 0};      // per output parity: [half4][8][9] complex, -c_mu/2 and phases folded in
+  bool has_clover = false;
+  void* clov[2] = {0, 0};       // per parity: [72][half4] reals
+  void* clov_inv[2] = {0, 0};
+  void* s_coef = 0;             // Moebius tridiagonal tables [3 kinds][2 dag][5][Ls]
+  void* s_inv = 0;              // dense MooeeInv blocks [P+, P-, P+^T, P-^T][Ls][Ls]
+  cgptb_lattice* tmp_full[4] = {0, 0, 0, 0};
+  cgptb_lattice* tmp_half[4] = {0, 0, 0, 0};
+
+  int ls() const { return Ls > 0 ? Ls : 1; }
+  void check_field(const cgptb_lattice* l) const;
+  cgptb_lattice* tmp(int i, int cb);
+  void setup_mobius_tables();
+  void import_gauge(const cgptb_lattice* const U[4]);
+};
+
+namespace cgptb {
+void op_dhop(cgptb_fermion_operator* op, bool dag, const cgptb_lattice* in, cgptb_lattice* out);
+void op_meooe(cgptb_fermion_operator* op, bool dag, const cgptb_lattice* in, cgptb_lattice* out);
+void op_mooee(cgptb_fermion_operator* op, bool inverse, bool dag, bool acc, const cgptb_lattice* in, cgptb_lattice* out);
+void op_s_tridiag(cgptb_fermion_operator* op, int kind, bool dag, bool acc, const cgptb_lattice* in, cgptb_lattice* out);
+void op_s_dense(cgptb_fermion_operator* op, bool dag, const cgptb_lattice* in, cgptb_lattice* out);
+void op_apply(cgptb_fermion_operator* op, int opcode, const cgptb_lattice* src, cgptb_lattice* dst);
+}  // namespace cgptb

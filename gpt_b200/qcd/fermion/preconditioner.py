@@ -1,0 +1,25 @@
+"""even-odd preconditioners (lib/gpt/qcd/fermion/preconditioner/even_odd_sites.py:23-72)"""
+import gpt_b200 as g
+from gpt_b200.params import params_convention
+
+
+@params_convention(parity=None)
+def eo2(params):
+    parity = params["parity"] if params["parity"] is not None else g.odd
+
+    def instantiate(op):
+        return g.algorithms.preconditioner.schur_complement_two(op, lambda op: op.even_odd_sites_decomposed(parity))
+
+    return instantiate
+
+
+@params_convention(parity=None)
+def eo2_ne(params):
+    parity = params["parity"] if params["parity"] is not None else g.odd
+
+    def instantiate(op):
+        return g.algorithms.preconditioner.normal_equation(
+            g.algorithms.preconditioner.schur_complement_two(op, lambda op: op.even_odd_sites_decomposed(parity))
+        )
+
+    return instantiate

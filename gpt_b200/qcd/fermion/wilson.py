@@ -1,0 +1,24 @@
+"""g.qcd.fermion.wilson_clover (lib/gpt/qcd/fermion/wilson.py:115-148)"""
+import copy
+
+import gpt_b200 as g
+from gpt_b200.qcd.fermion.operator import fine_operator
+
+
+@g.params_convention(
+    kappa=None, mass=None, cF=1, use_legacy=False, boundary_phases=None, isAnisotropic=None,
+    csw_r=None, csw_t=None, nu=None, xi_0=None, n_rhs=1,
+)
+def wilson_clover(U, params):
+    params = copy.deepcopy(params)
+    if params["kappa"] is not None:
+        assert params["mass"] is None
+        params["mass"] = 1.0 / params["kappa"] / 2.0 - 4.0
+        del params["kappa"]
+    if params["n_rhs"] > 1:
+        raise NotImplementedError("multi-rhs Wilson-clover (n_rhs > 1) is a SURVEY 8(f1) next row")
+    params["multi_rhs"] = False
+    if params["boundary_phases"][-1] == 0.0:
+        raise NotImplementedError("open boundary conditions are a SURVEY 8(f2) next row")
+    assert params["cF"] == 1.0  # forbid usage of cF without open bc
+    return fine_operator("wilson_clover", U, params, otype=g.ot_vector_spin_color(4, 3))

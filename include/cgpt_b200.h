@@ -1,0 +1,159 @@
+/*
+  cgpt_b200.h -- C ABI of libcgpt_b200.so: the B200-native replacement for the fermion-operator hot path of
+  GPT's `cgpt` module (lehner/gpt).  Every entry point names the cgpt export it replaces
+  (file:line relative to the reference checkout).
+
+  Conventions (mirroring cgpt):
+    * handles are opaque pointers; create_* returns an owning handle, delete_* frees it;
+      operator inputs are borrowed for the call only, except U which is copied at create/update.
+    * every call returns 0 on success and non-zero on failure; cgptb_last_error() then returns the message
+      (cgpt: C++ throw std::string -> PyExc_RuntimeError, lib/cgpt/lib/exception.h:23-39).
+    * calls are made from one host thread per GPU; work is enqueued on the library stream and the call
+      returns without synchronising unless it has to hand a number back to the host.
+    * host-side field layout ("GPT order"): site index lexicographic with dimension 0 fastest (5d grids:
+      s is dimension 0), checkerboarded fields hold the sites of that parity in the same order; per site the
+      tensor elements row-major, complex interleaved (numpy complex64 / complex128).  This is the order of
+      `lattice[:]` in GPT (lib/cgpt/lib/lattice/implementation.h:246-281).
+*/
+#ifndef CGPT_B200_H
+#define CGPT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cgptb_lattice cgptb_lattice;
+typedef struct cgptb_fermion_operator cgptb_fermion_operator;
+
+enum { CGPTB_SINGLE = 0, CGPTB_DOUBLE = 1 };
+enum { CGPTB_EVEN = 0, CGPTB_ODD = 1, CGPTB_FULL = 2 };
+/* object types (lib/gpt/core/object_type): complex singlet, colour matrix, spin-colour vector */
+enum { CGPTB_OT_SINGLET = 1, CGPTB_OT_MCOLOR = 9, CGPTB_OT_VSPINCOLOR = 12 };
+enum { CGPTB_WILSON_CLOVER = 0, CGPTB_MOBIUS = 1 };
+
+/* opcodes: lib/cgpt/lib/operators/register.h:2-20 */
+enum {
+  CGPTB_OP_M = 2001, CGPTB_OP_Mdag = 2002, CGPTB_OP_Meooe = 2003, CGPTB_OP_MeooeDag = 2004,
+  CGPTB_OP_Mooee = 2005, CGPTB_OP_MooeeDag = 2006, CGPTB_OP_MooeeInv = 2007, CGPTB_OP_MooeeInvDag = 2008,
+  CGPTB_OP_Mdiag = 2009, CGPTB_OP_Dminus = 2010, CGPTB_OP_DminusDag = 2011,
+  CGPTB_OP_ImportPhysicalFermionSource = 2012, CGPTB_OP_ImportUnphysicalFermion = 2013,
+  CGPTB_OP_ExportPhysicalFermionSolution = 2014, CGPTB_OP_ExportPhysicalFermionSource = 2015,
+  CGPTB_OP_Dhop = 3001, CGPTB_OP_DhopEO = 3002, CGPTB_OP_DhopDag = 4001, CGPTB_OP_DhopEODag = 4002
+};
+
+/* ---- runtime ------------------------------------------------------------------------------------ */
+/* cgpt.init (lib/cgpt/lib/init.cc:26-103): select the CUDA device, create the library stream.       */
+int cgptb_init(int device);
+const char* cgptb_last_error(void);
+/* cgpt.accelerator_barrier (lib/cgpt/lib/util.cc:335-338)                                            */
+int cgptb_accelerator_barrier(void);
+/* make the library enqueue on an externally owned cudaStream_t (e.g. torch's current stream); 0 = own */
+int cgptb_set_stream(void* cuda_stream);
+void* cgptb_get_stream(void);
+/* CUDA-event stopwatch on the library stream (cgpt.time is host wall clock, lib/cgpt/lib/time.cc:79-81) */
+int cgptb_timer_start(void);
+int cgptb_timer_stop(double* milliseconds);
+int cgptb_device_info(int* sm_count, size_t* total_mem, int* cc_major, int* cc_minor);
+/* number of kernels this library has launched since init (for bench.py's gpu_launches) */
+uint64_t cgptb_launch_count(void);
+
+/* ---- lattices (storage seam; cgpt.create_lattice & co., lib/cgpt/lib/lattice.cc:42-210) ----------- */
+/* dims4 = local x,y,z,t extents (all even); Ls = 0 for a 4d grid, else the extent of the 5th dimension
+   (grid dimension 0, never checkerboarded: lib/gpt/core/grid.py:31-37); cb = CGPTB_EVEN/ODD for a field
+   on the red-black grid, CGPTB_FULL otherwise.                                                        */
+int cgptb_create_lattice(cgptb_lattice** out, const int dims4[4], int Ls, int precision, int otype, int cb);
+/* wrap externally owned device memory (e.g. a torch tensor's data_ptr) of cgptb_lattice_bytes() bytes */
+int cgptb_create_lattice_view(cgptb_lattice** out, const int dims4[4], int Ls, int precision, int otype, int cb,
+                              void* device_ptr);
+int cgptb_delete_lattice(cgptb_lattice* l);
+size_t cgptb_lattice_bytes(const cgptb_lattice* l);
+size_t cgptb_lattice_sites(const cgptb_lattice* l);
+void* cgptb_lattice_device_ptr(cgptb_lattice* l);
+/* cgpt.lattice_get_checkerboard / lattice_change_checkerboard (lattice.cc:189-210) */
+int cgptb_lattice_get_checkerboard(const cgptb_lattice* l);
+int cgptb_lattice_change_checkerboard(cgptb_lattice* l, int cb);
+/* cgpt.lattice_set_to_number with 0 (`lattice[:] = 0`), lattice.cc:86-99 */
+int cgptb_lattice_set_to_zero(cgptb_lattice* l);
+/* `lattice[:] = ndarray` / `ndarray = lattice[:]` through cgpt.lattice_memory_view
+   (lattice/implementation.h:246-281): host buffer in GPT order, nbytes = sites*otype*2*sizeof(real)   */
+int cgptb_lattice_import(cgptb_lattice* l, const void* host, size_t nbytes);
+int cgptb_lattice_export(const cgptb_lattice* l, void* host, size_t nbytes);
+/* same, but the buffer is DEVICE memory in GPT order (no PCIe copy) */
+int cgptb_lattice_import_device(cgptb_lattice* l, const void* dev, size_t nbytes);
+int cgptb_lattice_export_device(const cgptb_lattice* l, void* dev, size_t nbytes);
+/* cgpt.copy / cgpt.convert (lib/cgpt/lib/transform.cc:41-54,128-141) */
+int cgptb_lattice_copy(cgptb_lattice* dst, const cgptb_lattice* src);
+int cgptb_lattice_convert(cgptb_lattice* dst, const cgptb_lattice* src);
+/* cgpt.lattice_pick_checkerboard / lattice_set_checkerboard (lattice.cc:164-187) */
+int cgptb_lattice_pick_checkerboard(int cb, cgptb_lattice* half, const cgptb_lattice* full);
+int cgptb_lattice_set_checkerboard(cgptb_lattice* full, const cgptb_lattice* half);
+
+/* ---- vector kernels ------------------------------------------------------------------------------- */
+/* cgpt.lattice_axpy: r = a*x + y, a complex cast to field precision
+   (transform.cc:211-246, foundation/transform.h:233-248).  No synchronisation (accelerator_forNB).   */
+int cgptb_lattice_axpy(cgptb_lattice* r, double a_re, double a_im, const cgptb_lattice* x, const cgptb_lattice* y);
+/* g.axpy_norm2 (lib/gpt/core/transform.py:151-153) fused: r = a*x + y ; *norm2 = |r|^2 (double accumulate) */
+int cgptb_lattice_axpy_norm2(cgptb_lattice* r, double a_re, double a_im, const cgptb_lattice* x,
+                             const cgptb_lattice* y, double* norm2);
+/* cgpt.lattice_rank_inner_product (transform.cc:143-178; foundation/reduce.h:76-253): result[i*n_right+j] =
+   sum conj(left_i) right_j accumulated in complex double for both precisions (reduce.h:129); rank-local. */
+int cgptb_lattice_rank_inner_product(const cgptb_lattice* const* left, int n_left, const cgptb_lattice* const* right,
+                                     int n_right, double* result_re_im);
+/* cgpt.lattice_norm2 (transform.cc:199-209) */
+int cgptb_lattice_norm2(const cgptb_lattice* a, double* norm2);
+/* cgpt.lattice_inner_product_norm2 (transform.cc:180-197): ip = <a,b>, a2 = |a|^2 in one pass */
+int cgptb_lattice_inner_product_norm2(const cgptb_lattice* a, const cgptb_lattice* b, double* ip_re_im, double* a2);
+/* cgpt.eval restricted to linear combinations: dst (+)= sum_i c_i a_i
+   (lib/cgpt/lib/eval.cc:323-365, expression/linear_combination_implementation.h:154-192)               */
+int cgptb_lattice_lc(cgptb_lattice* dst, int accumulate, int n, const double* coef_re_im,
+                     const cgptb_lattice* const* a);
+/* cgpt.linear_combination (lib/cgpt/lib/basis.cc:146-173, foundation/basis.h:21-97):
+   r_i = sum_k Qt[i*n_basis+k] basis_k, Qt complex128 row-major                                          */
+int cgptb_linear_combination(cgptb_lattice* const* r, int n_r, const cgptb_lattice* const* basis, int n_basis,
+                             const double* Qt_re_im);
+/* lattice *= a  (cgpt.eval with a single scaled term onto itself) */
+int cgptb_lattice_scale(cgptb_lattice* l, double a_re, double a_im);
+/* g.slice(g.trace(a * g.adj(b)), 3) for spin-colour vectors: out[t] = sum_{x,y,z} <b(x,t), a(x,t)> (complex),
+   the building block of the pion correlator in README.md:163-166; out has 2*dims4[3] doubles            */
+int cgptb_lattice_slice_inner_product(const cgptb_lattice* b, const cgptb_lattice* a, double* out_re_im);
+
+/* ---- fermion operators (lib/cgpt/lib/operators.cc:34-107) ------------------------------------------ */
+typedef struct {
+  /* Wilson-clover: lib/cgpt/lib/operators/wilson_clover.h:28-39 */
+  double mass, csw_r, csw_t, cF, xi_0, nu;
+  int isAnisotropic;
+  /* Moebius: lib/cgpt/lib/operators/mobius.h:42-51 */
+  double mass_plus, mass_minus, M5, b, c;
+  int Ls;
+  /* both: 4 complex boundary phases (re,im) */
+  double boundary_phases[8];
+} cgptb_fermion_params;
+
+/* cgpt.create_fermion_operator(optype, prec, params): U = 4 colour-matrix lattices on the full 4d grid */
+int cgptb_create_fermion_operator(cgptb_fermion_operator** out, int optype, int precision,
+                                  const cgptb_fermion_params* params, const cgptb_lattice* const U[4]);
+/* cgpt.update_fermion_operator: re-import the gauge field */
+int cgptb_update_fermion_operator(cgptb_fermion_operator* op, const cgptb_lattice* const U[4]);
+/* cgpt.set_mass_fermion_operator (operators/implementation.h:21-45) */
+int cgptb_set_mass_fermion_operator(cgptb_fermion_operator* op, const cgptb_fermion_params* params);
+int cgptb_delete_fermion_operator(cgptb_fermion_operator* op);
+/* cgpt.apply_fermion_operator(op, opcode, src, dst) -- note (src, dst) order (operators.cc:96-107) */
+int cgptb_apply_fermion_operator(cgptb_fermion_operator* op, int opcode, const cgptb_lattice* src, cgptb_lattice* dst);
+
+/* ---- fused fast paths (same results as the opcode sequences they replace) ---------------------------- */
+/* Mpc / Mpc^dag of schur_complement_two (lib/gpt/algorithms/preconditioner/schur_complement_two.py:87-112):
+   o = i - Meooe MooeeInv Meooe MooeeInv i ; tmp = 2 work fields of the same shape                       */
+int cgptb_apply_schur_two(cgptb_fermion_operator* op, int dag, const cgptb_lattice* in, cgptb_lattice* out);
+/* inv.cg on Mpc^dag Mpc (lib/gpt/algorithms/inverter/cg.py:47-112 on normal_equation.py:44-45) run entirely on the
+   device: same update order, reductions in double, residual test every iteration; history receives
+   |r|^2 per iteration (cg.history), *iterations the count.                                               */
+int cgptb_cg_eo2_ne(cgptb_fermion_operator* op, cgptb_lattice* psi, const cgptb_lattice* src, double eps,
+                    int maxiter, double* history, int* iterations, int* converged);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

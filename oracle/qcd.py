@@ -125,14 +125,16 @@ def matrix_exp(x):
 
 
 def gauge_random(rng, dims4, scale=1.0, precision="double"):
-    """g.qcd.gauge.random(grid, rng, scale) -> list of 4 link fields [T,Z,Y,X,3,3]"""
-    cdt = np.complex128 if precision == "double" else np.complex64
+    """g.qcd.gauge.random(grid, rng, scale) -> list of 4 link fields [T,Z,Y,X,3,3]
+    (fields drawn on a double grid use the rng's default generators, i.e. grid_tag None == "double")"""
+    precision = None if precision == "double" else precision
+    cdt = np.complex128 if precision is None else np.complex64
     gens = [t.astype(cdt) for t in su3_generators()]
     U = []
     for mu in range(4):
         A = np.zeros(tuple(dims4[::-1]) + (3, 3), dtype=cdt)
         for ta in gens:
-            ca = rng.uniform_real(dims4, (), min=-0.5, max=0.5).astype(cdt)
+            ca = rng.uniform_real(dims4, (), min=-0.5, max=0.5, grid_tag=precision).astype(cdt)
             A = A + (cdt(scale) * ca)[..., None, None] * ta
         U.append(matrix_exp(A * 1j).astype(cdt))
     return U

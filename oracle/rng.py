@@ -247,14 +247,16 @@ class random:
             site[:, ridx] = flat
         return {"gen": random_bits(seeds, self.p), "site": site, "nred": nred, "nblocks": nblocks}
 
-    def _state(self, dims):
-        key = tuple(int(d) for d in dims)
+    def _state(self, dims, grid_tag):
+        # generators are kept per grid OBJECT (engine.h:82-99): two grids of equal dims (e.g. a single and a
+        # double precision one) each start from the same seed; `grid_tag` tells such grids apart
+        key = (tuple(int(d) for d in dims), grid_tag)
         if key not in self.prng:
-            self.prng[key] = self._setup(key)
+            self.prng[key] = self._setup(key[0])
         return self.prng[key]
 
-    def _sample(self, dims, tensor_shape, dist, dtype=np.complex128, **kw):
-        st = self._state(dims)
+    def _sample(self, dims, tensor_shape, dist, dtype=np.complex128, grid_tag=None, **kw):
+        st = self._state(dims, grid_tag)
         nel = int(np.prod(tensor_shape)) if len(tensor_shape) else 1
         n = st["nred"] * nel
         gen = st["gen"]

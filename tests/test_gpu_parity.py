@@ -1,0 +1,325 @@
+"""
+GPU parity tests: the CUDA path (through the C ABI, via the gpt_b200 host API) against the CPU oracle on the
+same seeded inputs, and against the reference's golden fingerprints
+(/root/reference/tests/qcd/fermion_operators.py:371-459).  Tolerances: 1e-12 relative (double), 1e-5 (single)
+as BASELINE.json's north_star states; fingerprints to 100*eps like the reference (fermion_operators.py:527).
+"""
+import numpy as np
+import pytest
+
+from oracle import qcd
+from oracle.rng import random as oracle_random
+from tests.util import from_spinor, rel, sites, to_links, to_spinor
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"double": 1e-12, "single": 1e-5}
+
+WILSON = dict(kappa=0.13500, csw_r=0.0, csw_t=0.0, xi_0=1.33111, nu=2.61, isAnisotropic=True, boundary_phases=[1.0, -1.0, 1.0, -1.0])
+CLOVER = dict(WILSON, csw_r=1.5, csw_t=1.951)
+MOBIUS = dict(mass=0.08, M5=1.8, b=1.5, c=0.5, Ls=12, boundary_phases=[1.0, -1.0, 1.0, -1.0])
+MOBIUS_AXIAL = dict(mass_plus=0.08, mass_minus=0.11, M5=1.8, b=1.5, c=0.5, Ls=12, boundary_phases=[1.0, -1.0, 1.0, -1.0])
+DIMS = [8, 8, 8, 16]
+
+
+@pytest.fixture(scope="module")
+def g():
+    import gpt_b200 as g
+
+    g.cgpt.init(0)
+    return g
+
+
+@pytest.fixture(scope="module")
+def fields():
+    # same draw order as tests/qcd/fermion_operators.py:849-884
+    rng = oracle_random("finger_print")
+    U = qcd.gauge_random(rng, DIMS)
+    d5 = [12] + DIMS
+    f = dict(U=U)
+    f["src5"], f["dst5"] = rng.cnormal(d5, (4, 3)), rng.cnormal(d5, (4, 3))
+    f["src4"], f["dst4"] = rng.cnormal(DIMS, (4, 3)), rng.cnormal(DIMS, (4, 3))
+    rng_w = oracle_random("finger_print")
+    qcd.gauge_random(rng_w, DIMS)
+    f["srcw"], f["dstw"] = rng_w.cnormal(DIMS, (4, 3)), rng_w.cnormal(DIMS, (4, 3))
+    return f
+
+
+def prec_of(g, name):
+    return g.double if name == "double" else g.single
+
+
+# ---------------------------------------------------------------------------------------------------------
+# storage seam
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["double", "single"])
+@pytest.mark.parametrize("five_d", [False, True])
+def test_import_export_checkerboard(g, fields, precision, five_d):
+    p = prec_of(g, precision)
+    src = fields["src5"] if five_d else fields["src4"]
+    dims = ([12] if five_d else []) + DIMS
+    grid = g.grid(dims, p)
+    l = to_spinor(g, grid, src)
+    back = l[:]
+    assert np.array_equal(back, sites(src, 2).astype(p.complex_dtype))  # bit exact round trip
+    grid_eo = grid.checkerboarded(g.redblack)
+    for cb in [g.even, g.odd]:
+        h = g.vspincolor(grid_eo)
+        g.pick_checkerboard(cb, h, l)
+        assert h.checkerboard() is cb
+        ref = qcd.pick_checkerboard(src, cb.tag, ls=five_d).reshape(-1, 4, 3).astype(p.complex_dtype)
+        assert np.array_equal(h[:], ref)
+    # set_checkerboard reassembles the field
+    l2 = g.vspincolor(grid)
+    l2[:] = 0
+    for cb in [g.even, g.odd]:
+        h = g.vspincolor(grid_eo)
+        g.pick_checkerboard(cb, h, l)
+        g.set_checkerboard(l2, h)
+    assert np.array_equal(l2[:], back)
+    # convert
+    q = g.single if precision == "double" else g.double
+    c = g.convert(l, q)
+    assert np.array_equal(c[:], back.astype(q.complex_dtype))
+
+
+@pytest.mark.parametrize("precision", ["double", "single"])
+def test_vector_kernels(g, fields, precision):
+    p = prec_of(g, precision)
+    grid = g.grid([12] + DIMS, p)
+    a_np = sites(fields["src5"], 2).astype(p.complex_dtype)
+    b_np = sites(fields["dst5"], 2).astype(p.complex_dtype)
+    a, b = g.vspincolor(grid), g.vspincolor(grid)
+    a[:] = a_np
+    b[:] = b_np
+    tol = 1e-14 if precision == "double" else 1e-6
+    ip = g.inner_product(a, b)
+    ref = np.vdot(a_np.astype(np.complex128), b_np.astype(np.complex128))
+    assert abs(ip - ref) / abs(ref) < 1e-13  # double accumulation for both precisions (reduce.h:129)
+    n2 = g.norm2(a)
+    assert abs(n2 - np.vdot(a_np.astype(np.complex128), a_np.astype(np.complex128)).real) / n2 < 1e-13
+    ipn = g.inner_product_norm2(a, b)
+    assert abs(ipn[0] - ref) / abs(ref) < 1e-13 and abs(ipn[1] - n2) / n2 < 1e-13
+    alpha = 0.37 - 1.21j
+    r = g.lattice(a)
+    g.axpy(r, alpha, a, b)
+    want = p.complex_dtype(alpha) * a_np + b_np
+    assert rel(r[:], want) < tol
+    r2 = g.lattice(a)
+    n = g.axpy_norm2(r2, alpha, a, b)
+    assert np.array_equal(r2[:], r[:])
+    assert abs(n - g.norm2(r)) / n < 1e-13
+    # aliasing as cg.py uses it: r = -a*mmp + r ; p = b*p + r
+    g.axpy(r, -0.25, a, r)
+    want = p.complex_dtype(-0.25) * a_np + want
+    assert rel(r[:], want) < tol
+    # expressions: psi += a*p, dst @= x - y, scaling
+    psi = g.copy(b)
+    psi += 0.5 * a
+    assert rel(psi[:], b_np + p.complex_dtype(0.5) * a_np) < tol
+    d = g.lattice(a)
+    d @= a - b
+    assert rel(d[:], a_np - b_np) < tol
+    d *= 2.0
+    assert rel(d[:], 2 * (a_np - b_np)) < tol
+    # linear_combination (basis.py:66-74)
+    Qt = np.array([[0.3 + 0.1j, -1.0], [2.0, 0.5j]])
+    out = [g.lattice(a), g.lattice(a)]
+    g.linear_combination(out, [a, b], Qt)
+    for i in range(2):
+        assert rel(out[i][:], Qt[i, 0] * a_np + Qt[i, 1] * b_np) < 10 * tol
+
+
+# ---------------------------------------------------------------------------------------------------------
+# operators against the oracle and the golden fingerprints
+# ---------------------------------------------------------------------------------------------------------
+def _ops4(g, fields, params, precision):
+    p = prec_of(g, precision)
+    grid = g.grid(DIMS, p)
+    U = to_links(g, grid, fields["U"])
+    w = g.qcd.fermion.wilson_clover(U, dict(params))
+    Uo = [u.astype(p.complex_dtype) for u in fields["U"]]
+    wo = qcd.wilson_clover(Uo, **params)
+    return grid, w, wo
+
+
+@pytest.mark.parametrize("precision", ["double", "single"])
+@pytest.mark.parametrize("name", ["wilson", "clover"])
+def test_wilson_clover_full(g, fields, name, precision):
+    params = WILSON if name == "wilson" else CLOVER
+    grid, w, wo = _ops4(g, fields, params, precision)
+    tol = TOL[precision]
+    src_np = fields["srcw"].astype(grid.precision.complex_dtype)
+    src = to_spinor(g, grid, src_np)
+    for tag, ref in [
+        ("M", wo.M(src_np)), ("Mdag", wo.Mdag(src_np)), ("Mdiag", wo.Mdiag(src_np)),
+        ("Dhop", wo.Dhop(src_np)), ("DhopDag", wo.Dhop(src_np, dag=True)),
+    ]:
+        op = {"M": w, "Mdag": w.adj(), "Mdiag": w.Mdiag, "Dhop": w.Dhop, "DhopDag": w.Dhop.adj()}[tag]
+        got = from_spinor(g(op * src), src_np)
+        assert rel(got, ref) < tol, tag
+    if precision == "double":
+        dst = to_spinor(g, grid, fields["dstw"])
+        golden = {"wilson": (-999.7564252326631 - 466.7758727463097j, -961.5053827614738 - 3468.430447866095j),
+                  "clover": (-946.8714968698364 - 427.1253034080037j, -908.620454398646 - 3428.779878527792j)}[name]
+        X = g.inner_product(dst, g(w * src))
+        assert abs(X - golden[0]) / abs(golden[0]) < 1e-13
+        X = g.inner_product(dst, g(w.Mdiag * src))
+        assert abs(X - golden[1]) / abs(golden[1]) < 1e-13
+
+
+@pytest.mark.parametrize("precision", ["double", "single"])
+@pytest.mark.parametrize("name", ["wilson", "clover"])
+def test_wilson_clover_eo(g, fields, name, precision):
+    params = WILSON if name == "wilson" else CLOVER
+    grid, w, wo = _ops4(g, fields, params, precision)
+    tol = TOL[precision]
+    e = qcd.eo_ops(wo)
+    src_np = fields["srcw"].astype(grid.precision.complex_dtype)
+    for cb in [g.even, g.odd]:
+        half_np = e.proj(src_np, cb.tag)
+        half = to_spinor(g, w.F_grid_eo, src_np, cb)
+        checks = [
+            (w.Meooe, e.Meooe(half_np, cb.tag)), (w.Meooe.adj(), e.Meooe(half_np, cb.tag, dag=True)),
+            (w.DhopEO, e.Meooe(half_np, cb.tag)),
+            (w.Mooee, e.Mooee(half_np)), (w.Mooee.adj(), e.Mooee(half_np, dag=True)),
+            (w.Mooee.inv(), e.MooeeInv(half_np)), (w.Mooee.adj().inv(), e.MooeeInv(half_np, dag=True)),
+        ]
+        for i, (op, ref) in enumerate(checks):
+            got = g(op * half)
+            assert rel(from_spinor(got, src_np), ref) < tol, (cb, i)
+        assert g(w.Meooe * half).checkerboard() is cb.inv()
+        assert g(w.Mooee * half).checkerboard() is cb
+
+
+def _ops5(g, fields, params, precision):
+    p = prec_of(g, precision)
+    grid = g.grid(DIMS, p)
+    U = to_links(g, grid, fields["U"])
+    m = g.qcd.fermion.mobius(U, dict(params))
+    Uo = [u.astype(p.complex_dtype) for u in fields["U"]]
+    mo = qcd.mobius(Uo, **params)
+    return grid, m, mo
+
+
+@pytest.mark.parametrize("precision", ["double", "single"])
+@pytest.mark.parametrize("name", ["mobius", "axial"])
+def test_mobius_full(g, fields, name, precision):
+    params = MOBIUS if name == "mobius" else MOBIUS_AXIAL
+    grid, m, mo = _ops5(g, fields, params, precision)
+    tol = TOL[precision]
+    cdt = grid.precision.complex_dtype
+    s5 = fields["src5"].astype(cdt)
+    s4 = fields["src4"].astype(cdt)
+    src5 = to_spinor(g, m.F_grid, s5)
+    src4 = to_spinor(g, m.U_grid, s4)
+    checks5 = [
+        (m, mo.M(s5)), (m.adj(), mo.Mdag(s5)), (m.Mdiag, mo.Mdiag(s5)),
+        (m.Dhop, mo.Dhop(s5)), (m.Dhop.adj(), mo.Dhop(s5, dag=True)),
+        (m.Dminus, mo.Dminus(s5)), (m.Dminus.adj(), mo.Dminus(s5, dag=True)),
+    ]
+    for i, (op, ref) in enumerate(checks5):
+        assert rel(from_spinor(g(op * src5), s5), ref) < tol, i
+    assert rel(from_spinor(g(m.ImportPhysicalFermionSource * src4), s5), mo.ImportPhysicalFermionSource(s4)) < tol
+    assert rel(from_spinor(g(m.ImportUnphysicalFermion * src4), s5), mo.ImportUnphysicalFermion(s4)) < tol
+    assert rel(from_spinor(g(m.ExportPhysicalFermionSolution * src5), s4), mo.ExportPhysicalFermionSolution(s5)) < tol
+    assert rel(from_spinor(g(m.ExportPhysicalFermionSource * src5), s4), mo.ExportPhysicalFermionSource(s5)) < tol
+    if precision == "double":
+        dst5 = to_spinor(g, m.F_grid, fields["dst5"])
+        golden = {
+            "mobius": (-8693.09425573421 - 4130.7793316734915j, -4966.960264746144 - 2525.83968136146j, -97.93443075273976 - 690.6405168964976j),
+            "axial": (-8690.547330400455 - 4127.148886222195j, -4967.102993398692 - 2525.589904941078j, -97.93443075274081 - 690.6405168964941j),
+        }[name]
+        for op, s, ref in [(m, src5, golden[0]), (m.Mdiag, src5, golden[1]), (m.ImportPhysicalFermionSource, src4, golden[2])]:
+            X = g.inner_product(dst5, g(op * s))
+            assert abs(X - ref) / abs(ref) < 1e-13
+
+
+@pytest.mark.parametrize("precision", ["double", "single"])
+def test_mobius_eo(g, fields, precision):
+    grid, m, mo = _ops5(g, fields, MOBIUS_AXIAL, precision)
+    tol = TOL[precision]
+    e = qcd.eo_ops(mo)
+    s5 = fields["src5"].astype(grid.precision.complex_dtype)
+    for cb in [g.even, g.odd]:
+        half_np = e.proj(s5, cb.tag)
+        half = to_spinor(g, m.F_grid_eo, s5, cb)
+        checks = [
+            (m.Meooe, e.Meooe(half_np, cb.tag)), (m.Meooe.adj(), e.Meooe(half_np, cb.tag, dag=True)),
+            (m.DhopEO, e.proj(mo.Dhop(half_np), 1 - cb.tag)), (m.DhopEO.adj(), e.proj(mo.Dhop(half_np, dag=True), 1 - cb.tag)),
+            (m.Mooee, e.Mooee(half_np)), (m.Mooee.adj(), e.Mooee(half_np, dag=True)),
+            (m.Mooee.inv(), e.MooeeInv(half_np)), (m.Mooee.adj().inv(), e.MooeeInv(half_np, dag=True)),
+        ]
+        for i, (op, ref) in enumerate(checks):
+            assert rel(from_spinor(g(op * half), s5), ref) < tol, (cb, i)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Schur complement + CG: same iteration count and residual history as the oracle's cg.py restatement
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("kind", ["mobius", "clover"])
+def test_eo2_ne_cg_double(g, fields, kind, fused, monkeypatch):
+    if not fused:
+        monkeypatch.setenv("GPT_B200_NO_FUSED", "1")
+    small = [4, 4, 4, 8]
+    rng = oracle_random("cg_test")
+    U = qcd.gauge_random(rng, small, scale=0.5)
+    grid = g.grid(small, g.double)
+    Ug = to_links(g, grid, U)
+    if kind == "mobius":
+        params = dict(mass=0.1, M5=1.8, b=1.5, c=0.5, Ls=6, boundary_phases=[1.0, 1.0, 1.0, -1.0])
+        op, oo = g.qcd.fermion.mobius(Ug, dict(params)), qcd.mobius(U, **params)
+        src_np = rng.cnormal([6] + small, (4, 3))
+    else:
+        params = dict(mass=0.2, csw_r=1.1, csw_t=1.3, xi_0=1.0, nu=1.0, isAnisotropic=False, boundary_phases=[1.0, 1.0, 1.0, -1.0])
+        op, oo = g.qcd.fermion.wilson_clover(Ug, dict(params)), qcd.wilson_clover(U, **params)
+        src_np = rng.cnormal(small, (4, 3))
+    eps, maxiter = 1e-8, 500
+    ref, hist_ref = qcd.solve_eo2_ne(oo, src_np, eps, maxiter)
+    inv = g.algorithms.inverter
+    cg = inv.cg(eps=eps, maxiter=maxiter)
+    slv = inv.preconditioned(g.qcd.fermion.preconditioner.eo2_ne(), cg)(op)
+    src = to_spinor(g, op.F_grid, src_np)
+    dst = g(slv * src)
+    assert len(cg.history) == len(hist_ref)  # identical iteration count
+    assert np.allclose(cg.history, hist_ref, rtol=1e-6)
+    assert rel(from_spinor(dst, src_np), ref) < 1e-10
+    # true residual
+    r = g(op * dst - src)
+    assert (g.norm2(r) / g.norm2(src)) ** 0.5 < 1e-6
+
+
+def test_mixed_precision_defect_correction(g, fields):
+    # pattern of /root/reference/tests/manual/mpi.py:104-110 and tests/algorithms/solvers.py:112-118
+    small = [4, 4, 4, 8]
+    rng = oracle_random("cg_test")
+    U = qcd.gauge_random(rng, small, scale=0.5)
+    grid = g.grid(small, g.double)
+    Ug = to_links(g, grid, U)
+    params = dict(mass=0.2, csw_r=1.1, csw_t=1.3, xi_0=1.0, nu=1.0, isAnisotropic=False, boundary_phases=[1.0, 1.0, 1.0, -1.0])
+    op = g.qcd.fermion.wilson_clover(Ug, dict(params))
+    src_np = rng.cnormal(small, (4, 3))
+    src = to_spinor(g, grid, src_np)
+    inv = g.algorithms.inverter
+    pc = g.qcd.fermion.preconditioner
+    cg = inv.cg(eps=1e-4, maxiter=500)
+    dc = inv.defect_correcting(inv.mixed_precision(inv.preconditioned(pc.eo2_ne(), cg), g.single, g.double), eps=1e-10, maxiter=20)
+    dst = g(dc(op) * src)
+    r = g(op * dst - src)
+    assert (g.norm2(r) / g.norm2(src)) ** 0.5 < 1e-10
+    assert len(dc.history) >= 2
+
+
+def test_errors(g):
+    grid = g.grid([4, 4, 4, 4], g.double)
+    a = g.vspincolor(grid)
+    b = g.vspincolor(g.grid([4, 4, 4, 8], g.double))
+    with pytest.raises(RuntimeError):
+        g.axpy(a, 1.0, a, b)
+    with pytest.raises(Exception):
+        g.qcd.fermion.mobius(g.qcd.gauge.unit(grid), {"bogus": 1})
+    with pytest.raises(ValueError):
+        g.grid([4, 4, 4], g.double)
+    with pytest.raises(RuntimeError):
+        g.vspincolor(g.grid([3, 4, 4, 4], g.double))

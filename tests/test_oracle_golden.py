@@ -1,0 +1,121 @@
+"""
+CPU tests: pin the oracle against every golden vector the reference's own tests hold for the hot path.
+  /root/reference/tests/random/simple.py:18-31,69-144        RNG known-answer vectors
+  /root/reference/tests/qcd/fermion_operators.py:371-459     operator fingerprints <dst| M |src>
+"""
+import numpy as np
+import pytest
+
+from oracle import qcd
+from oracle.rng import random
+
+
+def test_rng_normal_kat():
+    rng = random("block_seed_string_13")
+    v = rng.normal([8, 4, 4, 4])
+
+    def at(x, y, z, t):
+        return v[t, z, y, x].real
+
+    got = np.array([at(0, 0, 0, 0), at(2, 0, 0, 0), at(0, 2, 0, 0), at(1, 3, 1, 3), at(3, 2, 1, 0)])
+    ref = np.array([-0.29101665386129116, -1.4591269443435488, -0.3641310411719848, -0.9454532383815435, 0.4996115272362977])
+    assert np.linalg.norm(got - ref) < 1e-14
+    for _ in range(1000):
+        v = rng.normal([8, 4, 4, 4])
+    got = np.array([at(0, 0, 0, 0), at(2, 0, 0, 0), at(0, 2, 0, 0), at(1, 3, 1, 3), at(3, 2, 1, 0)])
+    ref = np.array([1.473846437649123, 0.06134886004475955, -1.4849224560837744, -0.2316303634513769, -0.5309613807759392])
+    assert np.linalg.norm(got - ref) < 1e-14
+
+
+def test_rng_plaquette_kat():
+    # simple.py:18-27 : same rng object walks through three grids
+    rng = random("block_seed_string_13")
+    for dims, prec, ref, scale, precision in [
+        ([8, 4, 4, 4], 1e-28, -0.00014108397456619623, 10, "double"),
+        ([8, 4, 4, 4], 1e-14, -0.00014108397456619623, 10, "single"),
+        ([8, 8, 4, 8], 1e-28, 0.38723058417632267, 2, "double"),
+    ]:
+        U = qcd.gauge_random(rng, dims, scale=scale, precision=precision)
+        assert abs(qcd.plaquette(U) - ref) ** 2.0 < prec
+        for u in U:
+            eye = np.zeros_like(u)
+            eye[..., range(3), range(3)] = 1
+            assert np.sum(np.abs(qcd.adj(u) @ u - eye) ** 2) / np.sum(np.abs(u) ** 2) < prec
+
+
+def test_rng_scalar_choice_kat():
+    # simple.py:33-66,132-144: 10000 zn(2), 10000 zn(3), 10000 normal, one lattice normal x1001, then choice
+    rng = random("block_seed_string_13")
+    for _ in range(10000):
+        rng.scalar_zn(2)
+    for _ in range(10000):
+        rng.scalar_zn(3)
+    for _ in range(10000):
+        rng.scalar_normal()
+    assert rng.choice(["A", "B", "C"], 10) == ["C", "C", "A", "C", "C", "B", "A", "B", "C", "A"]
+    assert rng.choice([1, 2, 3], 5) == [2, 3, 3, 3, 1]
+
+
+@pytest.fixture(scope="module")
+def fingerprint_fields():
+    # tests/qcd/fermion_operators.py:849-884: U, then for grid in [F_grid, U_grid]: src, dst
+    dims = [8, 8, 8, 16]
+    rng = random("finger_print")
+    U = qcd.gauge_random(rng, dims)
+    d5 = [12] + dims
+    src5, dst5 = rng.cnormal(d5, (4, 3)), rng.cnormal(d5, (4, 3))
+    src4, dst4 = rng.cnormal(dims, (4, 3)), rng.cnormal(dims, (4, 3))
+    # Wilson tests: F_grid == U_grid, so the 4d fields are the FIRST draws after U
+    rng_w = random("finger_print")
+    Uw = qcd.gauge_random(rng_w, dims)
+    srcw, dstw = rng_w.cnormal(dims, (4, 3)), rng_w.cnormal(dims, (4, 3))
+    return dict(U=U, src5=src5, dst5=dst5, src4=src4, dst4=dst4, Uw=Uw, srcw=srcw, dstw=dstw)
+
+
+def _close(x, ref):
+    return abs(x - ref) / abs(ref) < 1e-13  # finger_print_tolerance * eps (fermion_operators.py:527,892-908)
+
+
+WILSON = dict(kappa=0.13500, csw_r=0.0, csw_t=0.0, xi_0=1.33111, nu=2.61, isAnisotropic=True, boundary_phases=[1.0, -1.0, 1.0, -1.0])
+CLOVER = dict(WILSON, csw_r=1.5, csw_t=1.951)
+MOBIUS = dict(mass=0.08, M5=1.8, b=1.5, c=0.5, Ls=12, boundary_phases=[1.0, -1.0, 1.0, -1.0])
+MOBIUS_AXIAL = dict(mass_plus=0.08, mass_minus=0.11, M5=1.8, b=1.5, c=0.5, Ls=12, boundary_phases=[1.0, -1.0, 1.0, -1.0])
+
+
+def test_wilson_fingerprints(fingerprint_fields):
+    f = fingerprint_fields
+    w = qcd.wilson_clover(f["Uw"], **WILSON)
+    assert _close(qcd.inner_product(f["dstw"], w.M(f["srcw"])), -999.7564252326631 - 466.7758727463097j)
+    assert _close(qcd.inner_product(f["dstw"], w.Mdiag(f["srcw"])), -961.5053827614738 - 3468.430447866095j)
+    w = qcd.wilson_clover(f["Uw"], **CLOVER)
+    assert _close(qcd.inner_product(f["dstw"], w.M(f["srcw"])), -946.8714968698364 - 427.1253034080037j)
+    assert _close(qcd.inner_product(f["dstw"], w.Mdiag(f["srcw"])), -908.620454398646 - 3428.779878527792j)
+
+
+def test_mobius_fingerprints(fingerprint_fields):
+    f = fingerprint_fields
+    m = qcd.mobius(f["U"], **MOBIUS)
+    assert _close(qcd.inner_product(f["dst5"], m.M(f["src5"])), -8693.09425573421 - 4130.7793316734915j)
+    assert _close(qcd.inner_product(f["dst5"], m.Mdiag(f["src5"])), -4966.960264746144 - 2525.83968136146j)
+    assert _close(qcd.inner_product(f["dst5"], m.ImportPhysicalFermionSource(f["src4"])), -97.93443075273976 - 690.6405168964976j)
+    m = qcd.mobius(f["U"], **MOBIUS_AXIAL)
+    assert _close(qcd.inner_product(f["dst5"], m.M(f["src5"])), -8690.547330400455 - 4127.148886222195j)
+    assert _close(qcd.inner_product(f["dst5"], m.Mdiag(f["src5"])), -4967.102993398692 - 2525.589904941078j)
+    assert _close(qcd.inner_product(f["dst5"], m.ImportPhysicalFermionSource(f["src4"])), -97.93443075274081 - 690.6405168964941j)
+
+
+def test_oracle_structure(fingerprint_fields):
+    # adjoint consistency, inverse, eo projection (fermion_operators.py:677-743)
+    f = fingerprint_fields
+    m = qcd.mobius(f["U"], **MOBIUS_AXIAL)
+    a = qcd.inner_product(f["dst5"], m.M(f["src5"]))
+    b = qcd.inner_product(m.Mdag(f["dst5"]), f["src5"])
+    assert abs(a - b) / abs(a) < 1e-13
+    x = m.MooeeInv(m.Mooee(f["src5"]))
+    assert np.linalg.norm(x - f["src5"]) / np.linalg.norm(f["src5"]) < 1e-13
+    # M restricted to parities equals Meooe + Mooee
+    e = qcd.eo_ops(m)
+    se = e.proj(f["src5"], 0)
+    full = m.M(se)
+    assert np.linalg.norm(e.proj(full, 1) - e.Meooe(se, 0)) / np.linalg.norm(full) < 1e-13
+    assert np.linalg.norm(e.proj(full, 0) - e.Mooee(se)) / np.linalg.norm(full) < 1e-13
