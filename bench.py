@@ -51,7 +51,7 @@ class clock_sampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -165,11 +165,11 @@ def run_native(args):
         if dist is not None:
             dist.barrier()
 
+    sampler = clock_sampler(local_rank)
     for _ in range(args.warmup):
         qm.Dhop.mat(dst, src)
     sync()
-    sampler = clock_sampler(local_rank)
-    time.sleep(0.3)
+    time.sleep(1.0)  # let nvidia-smi start sampling
     l0 = cgpt.launch_count()
     t0 = time.time()
     cgpt.timer_start()
@@ -242,7 +242,7 @@ def run_native(args):
                        "parallelism": f"T-split x{world}"},
             "gbs_effective_gpt_convention": eff_bytes * world / (ms_per_step * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k_dhop<float>", "peak_source": peak_src,
+                         "traffic": traffic, "kernel": "k_dhop_f32 (packed FFMA2 stencil, one launch per parity)", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_per_launch, "launches_per_step": launches_per_step},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
@@ -314,7 +314,7 @@ def run_reference(args):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-e2e", action="store_true")

@@ -202,7 +202,7 @@ class lattice:
     def __getitem__(self, key):
         a = np.empty(self._host_shape(), dtype=self.grid.precision.complex_dtype)
         cgpt.lattice_export(self.obj, a)
-        if isinstance(key, slice) and key == slice(None):
+        if isinstance(key, builtins.slice) and key == builtins.slice(None):
             return a
         if isinstance(key, tuple) and len(key) == self.grid.nd and all(isinstance(k, (int, np.integer)) for k in key):
             assert self.grid.cb.n == 1
@@ -213,7 +213,7 @@ class lattice:
         raise NotImplementedError("lattice[...] supports [:] and full-lattice point access")
 
     def __setitem__(self, key, value):
-        if isinstance(key, slice) and key == slice(None):
+        if isinstance(key, builtins.slice) and key == builtins.slice(None):
             if isinstance(value, numbers.Number) and value == 0:
                 cgpt.lattice_set_to_zero(self.obj)
                 return
@@ -584,7 +584,7 @@ class mspincolor:
             c[:] = 0
 
     def __getitem__(self, key):
-        if isinstance(key, slice) and key == slice(None):
+        if isinstance(key, builtins.slice) and key == builtins.slice(None):
             # [site, spin_i, spin_j, color_a, color_b] like GPT's mspincolor tensor
             cols = np.stack([c[:] for c in self.columns], axis=-1)  # [site, 4, 3, 12]
             n = cols.shape[0]

@@ -3,6 +3,7 @@
 // they dispatch to (lib/cgpt/lib/operators/unary.h:20-48, register.h:2-20):
 //   Dhop/DhopEO(+Dag), Meooe(+Dag), Mooee(+Dag), MooeeInv(+Dag), M, Mdag, Mdiag, Dminus(+Dag),
 //   Import/Export{Physical,Unphysical}Fermion{Source,Solution}.
+#include <stdlib.h>
 #include "operator.cuh"
 #include "dslash.cuh"
 
@@ -69,6 +70,15 @@ __global__ void __launch_bounds__(128) k_dhop(Geom g, int ls, int p_out, const T
   store_spinor(out, out_stride, tid, acc);
 }
 
+void dhop_half_f32(cgptb_fermion_operator* op, bool dag, const float* pin, size_t in_stride, float* pout, size_t out_stride,
+                   int p_out);  // dslash_f32.cu
+
+static bool use_generic_dhop() {
+  static int v = -1;
+  if (v < 0) v = getenv("CGPTB_GENERIC_DHOP") ? 1 : 0;
+  return v == 1;
+}
+
 // out(parity p_out) = Dhop in(parity 1-p_out); in/out given as (lattice, parity half to use)
 template <typename T>
 static void dhop_half(cgptb_fermion_operator* op, bool dag, const cgptb_lattice* in, cgptb_lattice* out, int p_out) {
@@ -79,6 +89,10 @@ static void dhop_half(cgptb_fermion_operator* op, bool dag, const cgptb_lattice*
   const size_t blk_reals = 16 / sizeof(T);
   if (in->cb == CGPTB_FULL) pin += (size_t)(1 - p_out) * half * blk_reals;
   if (out->cb == CGPTB_FULL) pout += (size_t)p_out * half * blk_reals;
+  if (sizeof(T) == 4 && !use_generic_dhop()) {
+    dhop_half_f32(op, dag, (const float*)pin, in->sites, (float*)pout, out->sites, p_out);
+    return;
+  }
   int threads = 128;
   unsigned blocks = (unsigned)((half + threads - 1) / threads);
   if (dag)
