@@ -1,16 +1,32 @@
-// Single-precision Wilson / Moebius hopping kernel on the packed FFMA2 pipe (sm_100a).
+// Single-precision Wilson / Moebius hopping kernels on the packed FFMA2 pipe (sm_100a).
 //
-// Same operator, layout and thread mapping as the generic k_dhop (operator.cu): one thread per output
-// (4d site, s), the Ls threads of a 4d site share its eight links.  All complex arithmetic is done on
-// (re, im) register pairs: a complex multiply-add is two FFMA2, spin projection and reconstruction are FADD2
-// with swap / negate operand modifiers, so the kernel issues ~430 packed FP instructions per site instead
-// of ~770 scalar ones -- which is what keeps the 5d fp32 stencil under the HBM roofline instead of the
-// FP32 issue limit (SURVEY.md section 7 "hard parts").
+// All complex arithmetic is done on (re, im) register pairs: a complex multiply-add is two FFMA2, spin
+// projection and reconstruction are FADD2 with swap / negate operand modifiers, so the kernel issues ~430
+// packed FP instructions per site instead of ~770 scalar ones (SURVEY.md section 7 "hard parts").
+//
+// k_dhop_f32_tiled (the production kernel):
+//   * one CTA = one 4d tile of NS checkerboard sites (default 4x4x2x2 in x,y,z,t = 32 sites of one parity)
+//     times all Ls slices, one thread per output (site, s); the neighbours of a tile overlap heavily, so the
+//     unified L1 serves about half of the 8 neighbour reads;
+//   * the tile's 8 x NS gauge links are staged once into shared memory (padded so the 3-4 distinct link
+//     addresses a warp reads land in different banks) and broadcast from there -- in the untiled kernel
+//     link loads through L1 were 45 % of all L1 wavefronts;
+//   * CTAs walk the lattice in z-slabs (x, y, z-in-slab, t, slab): the +-t neighbour reuse distance shrinks
+//     from a whole time slice to a slab of it and stays resident in L2; outputs are written with streaming
+//     stores so they do not evict the input window.
+// k_dhop_f32 (fallback for extents the tile does not divide): same arithmetic, linear site order.
+#include <stdio.h>
+#include <stdlib.h>
 #include "dslash.cuh"
 #include "operator.cuh"
 #include "packed.cuh"
 
 namespace cgptb {
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
 
 __device__ __forceinline__ void load_spinor_c32(const float* __restrict__ base, size_t nsites, size_t site, c32 (&p)[12]) {
   const float4* b = reinterpret_cast<const float4*>(base);
@@ -22,6 +38,7 @@ __device__ __forceinline__ void load_spinor_c32(const float* __restrict__ base, 
   }
 }
 
+template <bool STREAM>
 __device__ __forceinline__ void store_spinor_c32(float* __restrict__ base, size_t nsites, size_t site, const c32 (&p)[12]) {
   float4* b = reinterpret_cast<float4*>(base);
 #pragma unroll
@@ -29,27 +46,18 @@ __device__ __forceinline__ void store_spinor_c32(float* __restrict__ base, size_
     float4 v;
     upk(p[2 * k], v.x, v.y);
     upk(p[2 * k + 1], v.z, v.w);
-    b[k * nsites + site] = v;
+    if (STREAM)
+      __stcs(b + k * nsites + site, v);
+    else
+      b[k * nsites + site] = v;
   }
 }
 
+// one direction: acc += recon( W(^dag) proj psi(neighbour) ), link given as 9 (re,im) pairs
 template <int MU, bool FWD, bool DAG>
-__device__ __forceinline__ void hop_c32(c32 (&acc)[12], const Geom& g, int x, int y, int z, int t, int i4, int s, int ls,
-                                        const float* __restrict__ in, size_t in_stride, const float* __restrict__ links) {
+__device__ __forceinline__ void hop_core(c32 (&acc)[12], const c32 (&psi)[12], const float (&wr)[9], const float (&wi)[9]) {
   const int SGN = (FWD != DAG) ? -1 : +1;
   typedef Proj<MU, SGN> P;
-  int n4 = neighbor<MU, FWD>(g, x, y, z, t);
-  c32 psi[12];
-  load_spinor_c32(in, in_stride, (size_t)n4 * ls + s, psi);
-  // link elements as (re, im) scalars
-  float wr[9], wi[9];
-  const float2* lb = reinterpret_cast<const float2*>(links) + ((size_t)i4 * 8 + (FWD ? MU : MU + 4)) * 9;
-#pragma unroll
-  for (int k = 0; k < 9; k++) {
-    float2 v = __ldg(lb + k);
-    wr[k] = v.x;
-    wi[k] = v.y;
-  }
   c32 h[6];
 #pragma unroll
   for (int c = 0; c < 3; c++) {
@@ -83,7 +91,30 @@ __device__ __forceinline__ void hop_c32(c32 (&acc)[12], const Geom& g, int x, in
   }
 }
 
-template <bool DAG, int LS>
+template <int MU, bool FWD, bool DAG, int ABL = 0>
+__device__ __forceinline__ void hop_global_links(c32 (&acc)[12], const Geom& g, int x, int y, int z, int t, int i4, int s, int ls,
+                                                 const float* __restrict__ in, size_t in_stride, const float* __restrict__ links) {
+  int n4 = neighbor<MU, FWD>(g, x, y, z, t);
+  if (ABL == 1) n4 = i4;  // ablation: no neighbour traffic (every direction reads the site itself)
+  c32 psi[12];
+  load_spinor_c32(in, in_stride, (size_t)n4 * ls + s, psi);
+  if (ABL == 2) {  // ablation: no arithmetic
+#pragma unroll
+    for (int k = 0; k < 12; k++) acc[k] = add2(acc[k], psi[k]);
+    return;
+  }
+  float wr[9], wi[9];
+  const float2* lb = reinterpret_cast<const float2*>(links) + ((size_t)i4 * 8 + (FWD ? MU : MU + 4)) * 9;
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    float2 v = __ldg(lb + k);
+    wr[k] = v.x;
+    wi[k] = v.y;
+  }
+  hop_core<MU, FWD, DAG>(acc, psi, wr, wi);
+}
+
+template <bool DAG, int LS, int ABL = 0>
 __global__ void __launch_bounds__(128) k_dhop_f32(Geom g, int ls_rt, int p_out, const float* __restrict__ in, size_t in_stride,
                                                   float* __restrict__ out, size_t out_stride, const float* __restrict__ links) {
   const int ls = LS > 0 ? LS : ls_rt;
@@ -96,20 +127,149 @@ __global__ void __launch_bounds__(128) k_dhop_f32(Geom g, int ls_rt, int p_out, 
   c32 acc[12];
 #pragma unroll
   for (int k = 0; k < 12; k++) acc[k] = 0ull;
-  hop_c32<0, true, DAG>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
-  hop_c32<0, false, DAG>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
-  hop_c32<1, true, DAG>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
-  hop_c32<1, false, DAG>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
-  hop_c32<2, true, DAG>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
-  hop_c32<2, false, DAG>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
-  hop_c32<3, true, DAG>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
-  hop_c32<3, false, DAG>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
-  store_spinor_c32(out, out_stride, tid, acc);
+  hop_global_links<0, true, DAG, ABL>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
+  hop_global_links<0, false, DAG, ABL>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
+  hop_global_links<1, true, DAG, ABL>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
+  hop_global_links<1, false, DAG, ABL>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
+  hop_global_links<2, true, DAG, ABL>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
+  hop_global_links<2, false, DAG, ABL>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
+  hop_global_links<3, true, DAG, ABL>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
+  hop_global_links<3, false, DAG, ABL>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
+  store_spinor_c32<false>(out, out_stride, tid, acc);
+}
+
+// ---- tiled kernel ------------------------------------------------------------------------------------
+struct TileGeom {
+  int txh, ty, tz, tt;   // tile extents in checkerboard coordinates (xh = x/2)
+  int nxh, ny, nz, nt;   // tiles per dimension
+  int zslab;             // z-tiles per slab
+  int stream_stores;     // write the output with st.global.cs
+};
+
+static const int LINK_F4 = 37;  // float4 per site in shared memory: 36 (8 links x 72 B) + 1 pad -> 148 words, bank shift 20
+
+// link d of site l from shared memory; 72 B blocks are 16-byte aligned for even d, 8 mod 16 for odd d
+template <int D>
+__device__ __forceinline__ void load_link_smem(const float4* __restrict__ slinks, int l, float (&wr)[9], float (&wi)[9]) {
+  const float* base = reinterpret_cast<const float*>(slinks + l * LINK_F4) + D * 18;
+  float v[18];
+  if (D % 2 == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      float4 q = *reinterpret_cast<const float4*>(base + 4 * k);
+      v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+    }
+    float2 q = *reinterpret_cast<const float2*>(base + 16);
+    v[16] = q.x; v[17] = q.y;
+  } else {
+    float2 q = *reinterpret_cast<const float2*>(base);
+    v[0] = q.x; v[1] = q.y;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      float4 q4 = *reinterpret_cast<const float4*>(base + 2 + 4 * k);
+      v[2 + 4 * k] = q4.x; v[3 + 4 * k] = q4.y; v[4 + 4 * k] = q4.z; v[5 + 4 * k] = q4.w;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    wr[k] = v[2 * k];
+    wi[k] = v[2 * k + 1];
+  }
+}
+
+// one direction for the SPER s-slices a thread owns: the link is read once, the spinors are independent loads
+template <int MU, bool FWD, bool DAG, int LS, int SPER, int ABL>
+__device__ __forceinline__ void hop_tile(c32 (&acc)[SPER][12], const Geom& g, int x, int y, int z, int t, int l, int j, int i4,
+                                         const float* __restrict__ in, size_t in_stride, const float4* __restrict__ slinks) {
+  constexpr int TPS = LS / SPER;
+  int n4 = neighbor<MU, FWD>(g, x, y, z, t);
+  if (ABL == 1) n4 = i4;
+  c32 psi[SPER][12];
+#pragma unroll
+  for (int r = 0; r < SPER; r++) load_spinor_c32(in, in_stride, (size_t)n4 * LS + j + r * TPS, psi[r]);
+  if (ABL == 2) {
+#pragma unroll
+    for (int r = 0; r < SPER; r++)
+#pragma unroll
+      for (int k = 0; k < 12; k++) acc[r][k] = add2(acc[r][k], psi[r][k]);
+    return;
+  }
+  float wr[9], wi[9];
+  load_link_smem<FWD ? MU : MU + 4>(slinks, l, wr, wi);
+#pragma unroll
+  for (int r = 0; r < SPER; r++) hop_core<MU, FWD, DAG>(acc[r], psi[r], wr, wi);
+}
+
+template <bool DAG, int LS, int SPER, int NS, int MINB, int ABL = 0>
+__global__ void __launch_bounds__(NS* LS / SPER, MINB)
+    k_dhop_f32_tile(Geom g, TileGeom tg, int p_out, const float* __restrict__ in, size_t in_stride, float* __restrict__ out,
+                    size_t out_stride, const float* __restrict__ links) {
+  constexpr int TPS = LS / SPER;  // threads per 4d site
+  __shared__ __align__(16) float4 slinks[NS * LINK_F4];
+  // tile coordinates: x fastest, then y, z inside the slab, t, slab (the last slab may be narrower)
+  int b = blockIdx.x;
+  int bx = b % tg.nxh;
+  b /= tg.nxh;
+  int by = b % tg.ny;
+  b /= tg.ny;
+  int per_slab = tg.zslab * tg.nt;
+  int slab = b / per_slab;
+  int slab0 = slab * tg.zslab;
+  int zw = tg.zslab;
+  if (slab0 + zw > tg.nz) zw = tg.nz - slab0;
+  b -= slab * per_slab;
+  int bz = slab0 + b % zw;
+  int bt = b / zw;
+
+  const int l = threadIdx.x / TPS;
+  const int j = threadIdx.x - l * TPS;
+  int lx = l % tg.txh, r0 = l / tg.txh;
+  int ly = r0 % tg.ty;
+  r0 /= tg.ty;
+  int lz = r0 % tg.tz, lt = r0 / tg.tz;
+  const int xh = bx * tg.txh + lx, y = by * tg.ty + ly, z = bz * tg.tz + lz, t = bt * tg.tt + lt;
+  const int i4 = xh + g.hx * (y + g.L[1] * (z + g.L[2] * t));
+  const int x = 2 * xh + ((y + z + t + p_out) & 1);
+
+  // stage this site's 8 links (576 B) with the TPS threads that own it: 16-byte cp.async, L2 only
+  {
+    const float4* gl = reinterpret_cast<const float4*>(links) + (size_t)i4 * 36;
+    unsigned sbase = (unsigned)__cvta_generic_to_shared(slinks + l * LINK_F4);
+#pragma unroll
+    for (int m = j; m < 36; m += TPS)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + m * 16), "l"(gl + m));
+    asm volatile("cp.async.commit_group;");
+  }
+  c32 acc[SPER][12];
+#pragma unroll
+  for (int r = 0; r < SPER; r++)
+#pragma unroll
+    for (int k = 0; k < 12; k++) acc[r][k] = 0ull;
+  asm volatile("cp.async.wait_group 0;");
+  __syncthreads();
+  hop_tile<0, true, DAG, LS, SPER, ABL>(acc, g, x, y, z, t, l, j, i4, in, in_stride, slinks);
+  hop_tile<0, false, DAG, LS, SPER, ABL>(acc, g, x, y, z, t, l, j, i4, in, in_stride, slinks);
+  hop_tile<1, true, DAG, LS, SPER, ABL>(acc, g, x, y, z, t, l, j, i4, in, in_stride, slinks);
+  hop_tile<1, false, DAG, LS, SPER, ABL>(acc, g, x, y, z, t, l, j, i4, in, in_stride, slinks);
+  hop_tile<2, true, DAG, LS, SPER, ABL>(acc, g, x, y, z, t, l, j, i4, in, in_stride, slinks);
+  hop_tile<2, false, DAG, LS, SPER, ABL>(acc, g, x, y, z, t, l, j, i4, in, in_stride, slinks);
+  hop_tile<3, true, DAG, LS, SPER, ABL>(acc, g, x, y, z, t, l, j, i4, in, in_stride, slinks);
+  hop_tile<3, false, DAG, LS, SPER, ABL>(acc, g, x, y, z, t, l, j, i4, in, in_stride, slinks);
+#pragma unroll
+  for (int r = 0; r < SPER; r++) {
+    if (tg.stream_stores)
+      store_spinor_c32<true>(out, out_stride, (size_t)i4 * LS + j + r * TPS, acc[r]);
+    else
+      store_spinor_c32<false>(out, out_stride, (size_t)i4 * LS + j + r * TPS, acc[r]);
+  }
 }
 
 template <bool DAG>
-static void launch(int ls, unsigned blocks, int threads, const Geom& g, int p_out, const float* in, size_t is, float* out, size_t os,
-                   const float* links) {
+static void launch_linear(int ls, unsigned blocks, int threads, const Geom& g, int p_out, const float* in, size_t is, float* out,
+                          size_t os, const float* links) {
+  static int abl = env_int("CGPTB_ABLATE", 0);
+  if (ls == 12 && abl == 1) { k_dhop_f32<DAG, 12, 1><<<blocks, threads, 0, g_stream>>>(g, ls, p_out, in, is, out, os, links); return; }
+  if (ls == 12 && abl == 2) { k_dhop_f32<DAG, 12, 2><<<blocks, threads, 0, g_stream>>>(g, ls, p_out, in, is, out, os, links); return; }
   switch (ls) {
     case 1: k_dhop_f32<DAG, 1><<<blocks, threads, 0, g_stream>>>(g, ls, p_out, in, is, out, os, links); break;
     case 8: k_dhop_f32<DAG, 8><<<blocks, threads, 0, g_stream>>>(g, ls, p_out, in, is, out, os, links); break;
@@ -120,16 +280,86 @@ static void launch(int ls, unsigned blocks, int threads, const Geom& g, int p_ou
   }
 }
 
+// tile of NS checkerboard sites; returns false if the lattice is not divisible
+static bool make_tiles(const Geom& g, int ns, TileGeom& tg) {
+  // NS = 32: 2 x 4 x 2 x 2 (xh,y,z,t) ; NS = 16: 2 x 2 x 2 x 2 ; NS = 8: 1 x 2 x 2 x 2
+  static const char* tile_env = getenv("CGPTB_TILE");
+  int e[4];
+  if (tile_env && sscanf(tile_env, "%d,%d,%d,%d", &e[0], &e[1], &e[2], &e[3]) == 4 && e[0] * e[1] * e[2] * e[3] == ns) {
+    tg.txh = e[0]; tg.ty = e[1]; tg.tz = e[2]; tg.tt = e[3];
+  } else if (ns == 32) {
+    tg.txh = 4; tg.ty = 2; tg.tz = 2; tg.tt = 2;
+  } else if (ns == 16) {
+    tg.txh = 2; tg.ty = 2; tg.tz = 2; tg.tt = 2;
+  } else {
+    tg.txh = 1; tg.ty = 2; tg.tz = 2; tg.tt = 2;
+  }
+  if (g.hx % tg.txh || g.L[1] % tg.ty || g.L[2] % tg.tz || g.L[3] % tg.tt) return false;
+  tg.nxh = g.hx / tg.txh;
+  tg.ny = g.L[1] / tg.ty;
+  tg.nz = g.L[2] / tg.tz;
+  tg.nt = g.L[3] / tg.tt;
+  static int zslab_sites = env_int("CGPTB_ZSLAB", 16);  // slab width in z (sites)
+  static int stcs = env_int("CGPTB_STCS", 1);
+  tg.stream_stores = stcs;
+  tg.zslab = zslab_sites / tg.tz;
+  if (tg.zslab < 1) tg.zslab = 1;
+  if (tg.zslab > tg.nz) tg.zslab = tg.nz;
+  return true;
+}
+
+template <bool DAG, int LS, int SPER, int NS, int MINB>
+static bool launch_tile_t(const Geom& g, int p_out, const float* in, size_t is, float* out, size_t os, const float* links) {
+  TileGeom tg;
+  if (!make_tiles(g, NS, tg)) return false;
+  unsigned blocks = (unsigned)(tg.nxh * tg.ny * tg.nz * tg.nt);
+  static int abl = env_int("CGPTB_ABLATE", 0);
+  if (abl == 1)
+    k_dhop_f32_tile<DAG, LS, SPER, NS, MINB, 1><<<blocks, NS * LS / SPER, 0, g_stream>>>(g, tg, p_out, in, is, out, os, links);
+  else if (abl == 2)
+    k_dhop_f32_tile<DAG, LS, SPER, NS, MINB, 2><<<blocks, NS * LS / SPER, 0, g_stream>>>(g, tg, p_out, in, is, out, os, links);
+  else
+    k_dhop_f32_tile<DAG, LS, SPER, NS, MINB><<<blocks, NS * LS / SPER, 0, g_stream>>>(g, tg, p_out, in, is, out, os, links);
+  return true;
+}
+
+template <bool DAG>
+static bool launch_tiled(int ls, const Geom& g, int p_out, const float* in, size_t is, float* out, size_t os, const float* links) {
+  static int variant = env_int("CGPTB_DHOP_VARIANT", 0);
+  switch (ls) {
+    case 8: return launch_tile_t<DAG, 8, 1, 32, 2>(g, p_out, in, is, out, os, links);
+    case 12:
+      if (variant == 1) return launch_tile_t<DAG, 12, 1, 32, 2>(g, p_out, in, is, out, os, links);
+      if (variant == 2) return launch_tile_t<DAG, 12, 2, 32, 3>(g, p_out, in, is, out, os, links);
+      if (variant == 3) return launch_tile_t<DAG, 12, 3, 32, 2>(g, p_out, in, is, out, os, links);
+      if (variant == 4) return launch_tile_t<DAG, 12, 3, 32, 3>(g, p_out, in, is, out, os, links);
+      if (variant == 5) return launch_tile_t<DAG, 12, 2, 16, 4>(g, p_out, in, is, out, os, links);
+      if (variant == 6) return launch_tile_t<DAG, 12, 3, 16, 4>(g, p_out, in, is, out, os, links);
+      if (variant == 7) return launch_tile_t<DAG, 12, 2, 32, 2>(g, p_out, in, is, out, os, links);
+      return launch_tile_t<DAG, 12, 1, 32, 2>(g, p_out, in, is, out, os, links);
+    case 16: return launch_tile_t<DAG, 16, 1, 16, 2>(g, p_out, in, is, out, os, links);
+    case 24: return launch_tile_t<DAG, 24, 1, 16, 2>(g, p_out, in, is, out, os, links);
+    default: return false;
+  }
+}
+
 void dhop_half_f32(cgptb_fermion_operator* op, bool dag, const float* pin, size_t in_stride, float* pout, size_t out_stride,
                    int p_out) {
   int ls = op->ls();
-  size_t half = (size_t)op->g.half4 * ls;
-  int threads = 128;
-  unsigned blocks = (unsigned)((half + threads - 1) / threads);
-  if (dag)
-    launch<true>(ls, blocks, threads, op->g, p_out, pin, in_stride, pout, out_stride, (const float*)op->links[p_out]);
-  else
-    launch<false>(ls, blocks, threads, op->g, p_out, pin, in_stride, pout, out_stride, (const float*)op->links[p_out]);
+  static int no_tiles = env_int("CGPTB_NO_TILES", 0);
+  const float* links = (const float*)op->links[p_out];
+  bool done = false;
+  if (!no_tiles) done = dag ? launch_tiled<true>(ls, op->g, p_out, pin, in_stride, pout, out_stride, links)
+                            : launch_tiled<false>(ls, op->g, p_out, pin, in_stride, pout, out_stride, links);
+  if (!done) {
+    size_t half = (size_t)op->g.half4 * ls;
+    int threads = 128;
+    unsigned blocks = (unsigned)((half + threads - 1) / threads);
+    if (dag)
+      launch_linear<true>(ls, blocks, threads, op->g, p_out, pin, in_stride, pout, out_stride, links);
+    else
+      launch_linear<false>(ls, blocks, threads, op->g, p_out, pin, in_stride, pout, out_stride, links);
+  }
   LAUNCH_CHECK();
 }
 
