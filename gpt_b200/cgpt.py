@@ -47,6 +47,11 @@ SIGNATURES = {
     "cgptb_timer_stop": (c_int, [_pd]),
     "cgptb_device_info": (c_int, [_pi, ctypes.POINTER(c_size_t), _pi, _pi]),
     "cgptb_launch_count": (ctypes.c_uint64, []),
+    "cgptb_comm_unique_id": (c_int, [ctypes.c_char_p]),
+    "cgptb_comm_init": (c_int, [c_int, c_int, _pi, ctypes.c_char_p]),
+    "cgptb_comm_finalize": (c_int, []),
+    "cgptb_comm_info": (c_int, [_pi, _pi, _pi, _pi]),
+    "cgptb_comm_globalsum": (c_int, [_pd, c_int]),
     "cgptb_create_lattice": (c_int, [_pp, _pi, c_int, c_int, c_int, c_int]),
     "cgptb_create_lattice_view": (c_int, [_pp, _pi, c_int, c_int, c_int, c_int, c_void_p]),
     "cgptb_delete_lattice": (c_int, [c_void_p]),
@@ -155,6 +160,29 @@ def device_info():
 
 def launch_count():
     return int(_lib_ready().cgptb_launch_count())
+
+
+# ---- processor grid ------------------------------------------------------------------------------------
+def comm_unique_id():
+    buf = ctypes.create_string_buffer(128)
+    _check(_lib_ready().cgptb_comm_unique_id(buf))
+    return buf.raw
+
+
+def comm_init(rank, world, mpi, unique_id):
+    m = (c_int * 4)(*[int(x) for x in mpi])
+    _check(_lib_ready().cgptb_comm_init(int(rank), int(world), m, ctypes.create_string_buffer(unique_id, 128)))
+
+
+def comm_finalize():
+    if _lib is not None:
+        _lib.cgptb_comm_finalize()
+
+
+def comm_globalsum(values):
+    a = np.ascontiguousarray(np.array(values, dtype=np.float64).reshape(-1))
+    _check(_lib_ready().cgptb_comm_globalsum(a.ctypes.data_as(_pd), a.size))
+    return a
 
 
 # ---- lattices ----------------------------------------------------------------------------------------

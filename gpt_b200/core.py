@@ -84,15 +84,21 @@ class grid:
         self.precision = precision
         self.cb = full if cb is None else cb
         self.parent = parent
-        self.mpi = mpi if mpi is not None else [1] * self.nd
-        self.processor = 0
-        self.Nprocessors = 1
+        # processor grid over (x,y,z,t); the fifth dimension is never split (lib/gpt/core/grid.py:83-87)
+        from gpt_b200 import parallel
+
+        mpi4 = list(parallel.mpi) if mpi is None else list(mpi)[-4:]
+        self.mpi = ([1] if self.nd == 5 else []) + mpi4
+        self.processor = parallel.rank
+        self.Nprocessors = parallel.world
+        self.ldimensions = self.fdimensions[:-4] + parallel.local_dims(self.fdimensions[-4:], mpi4)
         self.gsites = int(np.prod(self.fdimensions))
         self.obj = self  # cgpt grid handles are not needed: a lattice carries its geometry
 
     @property
     def dims4(self):
-        return self.fdimensions[-4:]
+        """local x,y,z,t extents (what libcgpt_b200 sees)"""
+        return self.ldimensions[-4:]
 
     @property
     def Ls(self):
@@ -130,7 +136,13 @@ class grid:
         cgpt.accelerator_barrier()
 
     def globalsum(self, x):
-        return x
+        from gpt_b200 import parallel
+
+        return parallel.globalsum(x)
+
+    @property
+    def lsites(self):
+        return int(np.prod(self.ldimensions))
 
 
 # ---- object types ----------------------------------------------------------------------------------------------
@@ -512,20 +524,23 @@ def norm2(l):
     if isinstance(l, list):
         return [norm2(x) for x in l]
     l = eval(l)
-    return cgpt.lattice_norm2(l.obj)
+    return l.grid.globalsum(cgpt.lattice_norm2(l.obj))
 
 
 def inner_product(a, b):
     a, b = eval(a), eval(b)
-    return builtins.complex(cgpt.lattice_rank_inner_product([a.obj], [b.obj])[0, 0])
+    return a.grid.globalsum(builtins.complex(cgpt.lattice_rank_inner_product([a.obj], [b.obj])[0, 0]))
 
 
 def rank_inner_product(a, b, use_accelerator=True):
-    return inner_product(a, b)
+    """rank-local <a,b>; the caller does the global sum (lib/gpt/core/transform.py:101-110)"""
+    a, b = eval(a), eval(b)
+    return builtins.complex(cgpt.lattice_rank_inner_product([a.obj], [b.obj])[0, 0])
 
 
 def inner_product_norm2(a, b):
-    return cgpt.lattice_inner_product_norm2(a.obj, b.obj)
+    ip, n2 = cgpt.lattice_inner_product_norm2(a.obj, b.obj)
+    return a.grid.globalsum(ip), a.grid.globalsum(n2)
 
 
 def axpy(d, a, x, y):
@@ -533,7 +548,7 @@ def axpy(d, a, x, y):
 
 
 def axpy_norm2(d, a, x, y):
-    return cgpt.lattice_axpy_norm2(d.obj, a, x.obj, y.obj)
+    return d.grid.globalsum(cgpt.lattice_axpy_norm2(d.obj, a, x.obj, y.obj))
 
 
 def linear_combination(r, basis, Qt, n_block=8):
@@ -649,8 +664,8 @@ class _create:
         for d in reversed(range(gr.nd)):
             idx = idx * gr.fdimensions[d] + int(pos[d])
         for j, col in enumerate(src.columns):
-            a = np.zeros((gr.gsites, 4, 3), dtype=gr.precision.complex_dtype)
-            a.reshape(gr.gsites, 12)[idx, j] = 1.0
+            a = np.zeros((gr.lsites, 4, 3), dtype=gr.precision.complex_dtype)
+            a.reshape(gr.lsites, 12)[idx, j] = 1.0
             col[:] = a
         return src
 

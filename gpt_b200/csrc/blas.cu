@@ -12,6 +12,8 @@
 
 namespace cgptb {
 
+bool g_reduce_global = false;  // solver.cu: sum reduction results over all ranks before they reach the host
+
 static const int BT = 256;
 static const int UNROLL = 4;
 
@@ -193,6 +195,7 @@ static void axpy_t(cgptb_lattice* r, double are, double aim, const cgptb_lattice
   LAUNCH_CHECK();
   k_final<<<1, BT, 0, g_stream>>>((int)g, 1, part, out);
   LAUNCH_CHECK();
+  if (g_reduce_global) comm_allreduce_device(out, 1, g_stream);
   double* h = reduce_host(8);
   CUDA_CHECK(cudaMemcpyAsync(h, out, sizeof(double), cudaMemcpyDeviceToHost, g_stream));
   CUDA_CHECK(cudaStreamSynchronize(g_stream));
@@ -228,6 +231,7 @@ static void reduce_t(const cgptb_lattice* a, const cgptb_lattice* b, bool dot, b
   LAUNCH_CHECK();
   k_final<<<1, BT, 0, g_stream>>>((int)g, 3, part, out);
   LAUNCH_CHECK();
+  if (g_reduce_global) comm_allreduce_device(out, 3, g_stream);
   double* h = reduce_host(8);
   CUDA_CHECK(cudaMemcpyAsync(h, out, 3 * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
   CUDA_CHECK(cudaStreamSynchronize(g_stream));

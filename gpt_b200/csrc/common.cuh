@@ -23,6 +23,24 @@ extern thread_local std::string g_error;
 extern cudaStream_t g_stream;
 extern uint64_t g_launches;
 
+// processor grid (comm.cu); inactive for a single GPU
+struct Comm {
+  bool active = false;
+  int rank = 0, world = 1;
+  int pgrid[4] = {1, 1, 1, 1};
+  int pcoor[4] = {0, 0, 0, 0};
+  void* nccl = 0;
+  cudaStream_t stream = 0;
+  cudaEvent_t ev_pack = 0, ev_comm = 0;
+};
+extern Comm g_comm;
+int comm_neighbor_rank(int mu, int dir);
+void comm_exchange_begin();
+void comm_exchange_dir(int mu, const void* to_lo, const void* to_hi, void* from_lo, void* from_hi, size_t bytes, cudaStream_t s);
+void comm_exchange_end();
+void comm_allreduce_device(double* dev, int n, cudaStream_t s);
+extern bool g_reduce_global;
+
 struct Error {
   std::string msg;
 };
@@ -144,9 +162,10 @@ __device__ __forceinline__ size_t elem_offset(size_t nsites, size_t site, int c,
 
 // geometry of one parity of the local 4d lattice
 struct Geom {
-  int L[4];    // x,y,z,t
-  int hx;      // L[0]/2
-  int half4;   // sites per parity
+  int L[4];       // x,y,z,t (local extents)
+  int hx;         // L[0]/2
+  int half4;      // sites per parity
+  int comm_mask;  // bit mu set: direction mu is split across GPUs, hops leaving the local volume are skipped
 };
 
 inline Geom make_geom(const int dims4[4]) {
@@ -154,6 +173,7 @@ inline Geom make_geom(const int dims4[4]) {
   for (int i = 0; i < 4; i++) g.L[i] = dims4[i];
   g.hx = dims4[0] / 2;
   g.half4 = dims4[0] / 2 * dims4[1] * dims4[2] * dims4[3];
+  g.comm_mask = 0;
   return g;
 }
 

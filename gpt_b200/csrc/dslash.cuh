@@ -145,12 +145,21 @@ __device__ __forceinline__ int neighbor(const Geom& g, int x, int y, int z, int 
   return cb_index(g, c[0], c[1], c[2], c[3]);
 }
 
+// true if the hop in direction MU (forward / backward) leaves the local volume of a split direction
+template <int MU, bool FWD>
+__device__ __forceinline__ bool off_rank(const Geom& g, int x, int y, int z, int t) {
+  if (!((g.comm_mask >> MU) & 1)) return false;
+  int c = MU == 0 ? x : (MU == 1 ? y : (MU == 2 ? z : t));
+  return FWD ? c == g.L[MU] - 1 : c == 0;
+}
+
 // one direction of the stencil: acc += recon( W(^dag) proj psi(neighbour) )
 template <int MU, bool FWD, bool DAG, typename T>
 __device__ __forceinline__ void hop(T (&acc)[24], const Geom& g, int x, int y, int z, int t, int i4, int s, int ls,
                                     const T* __restrict__ in, size_t in_stride, const T* __restrict__ links) {
   // forward hop uses (1 - g_mu), backward (1 + g_mu); daggered operator swaps them
   const int SGN = (FWD != DAG) ? -1 : +1;
+  if (off_rank<MU, FWD>(g, x, y, z, t)) return;
   int n4 = neighbor<MU, FWD>(g, x, y, z, t);
   T psi[24], h[12], chi[12], W[18];
   load_spinor(in, in_stride, (size_t)n4 * ls + s, psi);

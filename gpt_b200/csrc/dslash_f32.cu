@@ -94,6 +94,7 @@ __device__ __forceinline__ void hop_core(c32 (&acc)[12], const c32 (&psi)[12], c
 template <int MU, bool FWD, bool DAG, int ABL = 0>
 __device__ __forceinline__ void hop_global_links(c32 (&acc)[12], const Geom& g, int x, int y, int z, int t, int i4, int s, int ls,
                                                  const float* __restrict__ in, size_t in_stride, const float* __restrict__ links) {
+  if (off_rank<MU, FWD>(g, x, y, z, t)) return;
   int n4 = neighbor<MU, FWD>(g, x, y, z, t);
   if (ABL == 1) n4 = i4;  // ablation: no neighbour traffic (every direction reads the site itself)
   c32 psi[12];
@@ -182,6 +183,7 @@ template <int MU, bool FWD, bool DAG, int LS, int SPER, int ABL>
 __device__ __forceinline__ void hop_tile(c32 (&acc)[SPER][12], const Geom& g, int x, int y, int z, int t, int l, int j, int i4,
                                          const float* __restrict__ in, size_t in_stride, const float4* __restrict__ slinks) {
   constexpr int TPS = LS / SPER;
+  if (off_rank<MU, FWD>(g, x, y, z, t)) return;
   int n4 = neighbor<MU, FWD>(g, x, y, z, t);
   if (ABL == 1) n4 = i4;
   c32 psi[SPER][12];

@@ -15,7 +15,7 @@ namespace cgptb {
 // ----------------------------------------------------------------------------------------------------
 template <typename TU, typename T>
 __global__ void k_build_links(Geom g, int p, size_t nsitesU, const TU* U0, const TU* U1, const TU* U2, const TU* U3,
-                              LinkCoef lc, T* __restrict__ links) {
+                              LinkCoef lc, T* __restrict__ links, const double* gh1, const double* gh2, const double* gh3) {
   int i4 = blockIdx.x * blockDim.x + threadIdx.x;
   if (i4 >= g.half4) return;
   int x, y, z, t;
@@ -25,18 +25,30 @@ __global__ void k_build_links(Geom g, int p, size_t nsitesU, const TU* U0, const
     int mu = d & 3;
     int c[4] = {x, y, z, t};
     int pp = p;
+    const double* ghost = 0;  // link owned by the rank-mu neighbour (split direction, low face)
+    int gc = c[mu] + lc.goff[mu];  // global coordinate of the link's site in direction mu
     if (d >= 4) {
+      if (c[mu] == 0 && ((g.comm_mask >> mu) & 1)) ghost = mu == 1 ? gh1 : (mu == 2 ? gh2 : gh3);
       c[mu] = c[mu] == 0 ? g.L[mu] - 1 : c[mu] - 1;
+      gc = (gc - 1 + lc.gL[mu]) % lc.gL[mu];
       pp = 1 - p;
     }
     size_t site = (size_t)pp * g.half4 + cb_index(g, c[0], c[1], c[2], c[3]);
+    size_t ft = 0;
+    if (ghost) {  // transverse lexicographic index on the face (x fastest), as written by k_pack_links
+      int o[2], n = 0;
+      for (int e = 1; e < 4; e++)
+        if (e != mu) o[n++] = e;
+      ft = c[0] + (size_t)g.L[0] * (c[o[0]] + (size_t)g.L[o[0]] * c[o[1]]);
+    }
     // phase multiplies U_mu on the last slice of direction mu (global coordinate)
-    bool last = (c[mu] + lc.goff[mu]) == lc.gL[mu] - 1;
+    bool last = gc == lc.gL[mu] - 1;
     double fr = lc.w[mu] * (last ? lc.ph[2 * mu] : 1.0);
     double fi = lc.w[mu] * (last ? lc.ph[2 * mu + 1] : 0.0);
     for (int k = 0; k < 9; k++) {
       size_t o = elem_offset<TU>(nsitesU, site, k, 1);
-      double ur = U[mu][o], ui = U[mu][o + 1];
+      double ur = ghost ? ghost[(ft * 9 + k) * 2] : (double)U[mu][o];
+      double ui = ghost ? ghost[(ft * 9 + k) * 2 + 1] : (double)U[mu][o + 1];
       links[((size_t)(i4 * 8 + d) * 9 + k) * 2] = (T)(fr * ur - fi * ui);
       links[((size_t)(i4 * 8 + d) * 9 + k) * 2 + 1] = (T)(fr * ui + fi * ur);
     }
@@ -89,17 +101,20 @@ static void dhop_half(cgptb_fermion_operator* op, bool dag, const cgptb_lattice*
   const size_t blk_reals = 16 / sizeof(T);
   if (in->cb == CGPTB_FULL) pin += (size_t)(1 - p_out) * half * blk_reals;
   if (out->cb == CGPTB_FULL) pout += (size_t)p_out * half * blk_reals;
+  // split lattice: faces go out first, the interior stencil hides the transfer, then the boundary update
+  if (op->g.comm_mask) halo_begin(op, dag, p_out, pin, in->sites);
   if (sizeof(T) == 4 && !use_generic_dhop()) {
     dhop_half_f32(op, dag, (const float*)pin, in->sites, (float*)pout, out->sites, p_out);
-    return;
+  } else {
+    int threads = 128;
+    unsigned blocks = (unsigned)((half + threads - 1) / threads);
+    if (dag)
+      k_dhop<T, true><<<blocks, threads, 0, g_stream>>>(op->g, ls, p_out, pin, in->sites, pout, out->sites, (const T*)op->links[p_out]);
+    else
+      k_dhop<T, false><<<blocks, threads, 0, g_stream>>>(op->g, ls, p_out, pin, in->sites, pout, out->sites, (const T*)op->links[p_out]);
+    LAUNCH_CHECK();
   }
-  int threads = 128;
-  unsigned blocks = (unsigned)((half + threads - 1) / threads);
-  if (dag)
-    k_dhop<T, true><<<blocks, threads, 0, g_stream>>>(op->g, ls, p_out, pin, in->sites, pout, out->sites, (const T*)op->links[p_out]);
-  else
-    k_dhop<T, false><<<blocks, threads, 0, g_stream>>>(op->g, ls, p_out, pin, in->sites, pout, out->sites, (const T*)op->links[p_out]);
-  LAUNCH_CHECK();
+  if (op->g.comm_mask) halo_end(op, dag, p_out, pout, out->sites);
 }
 
 void op_dhop(cgptb_fermion_operator* op, bool dag, const cgptb_lattice* in, cgptb_lattice* out) {
@@ -647,8 +662,8 @@ static void import_gauge_t(cgptb_fermion_operator* op, const cgptb_lattice* cons
     lc.w[mu] = -0.5 * (mu < 3 ? ani : 1.0);
     lc.ph[2 * mu] = op->p.boundary_phases[2 * mu];
     lc.ph[2 * mu + 1] = op->p.boundary_phases[2 * mu + 1];
-    lc.goff[mu] = 0;
-    lc.gL[mu] = op->dims4[mu];
+    lc.goff[mu] = op->goff[mu];
+    lc.gL[mu] = op->gL[mu];
   }
   size_t link_bytes = (size_t)op->g.half4 * 8 * 18 * sizeof(T);
   int threads = 128;
@@ -656,10 +671,13 @@ static void import_gauge_t(cgptb_fermion_operator* op, const cgptb_lattice* cons
   for (int p = 0; p < 2; p++) {
     if (!op->links[p]) CUDA_CHECK(cudaMalloc(&op->links[p], link_bytes));
     k_build_links<TU, T><<<blocks, threads, 0, g_stream>>>(op->g, p, U[0]->sites, (const TU*)U[0]->data, (const TU*)U[1]->data,
-                                                           (const TU*)U[2]->data, (const TU*)U[3]->data, lc, (T*)op->links[p]);
+                                                           (const TU*)U[2]->data, (const TU*)U[3]->data, lc, (T*)op->links[p],
+                                                           (const double*)op->ghost_links[1], (const double*)op->ghost_links[2],
+                                                           (const double*)op->ghost_links[3]);
     LAUNCH_CHECK();
   }
   op->has_clover = op->type == CGPTB_WILSON_CLOVER && (op->p.csw_r != 0.0 || op->p.csw_t != 0.0);
+  if (op->has_clover && op->g.comm_mask) CGPTB_ERR("the clover term on a split lattice is not implemented yet (needs corner halos of U)");
   if (op->has_clover) {
     CloverCoef cc;
     cc.diag = op->p.mass + 1.0 + 3.0 * op->p.nu / op->p.xi_0;
@@ -713,6 +731,7 @@ void cgptb_fermion_operator::import_gauge(const cgptb_lattice* const U[4]) {
       if (U[mu]->dims4[i] != dims4[i]) CGPTB_ERR("U[%d] lives on a different grid", mu);
     if (U[mu]->prec != U[0]->prec) CGPTB_ERR("gauge links have mixed precision");
   }
+  halo_setup(this, U);
   if (U[0]->prec == CGPTB_SINGLE) {
     if (prec == CGPTB_SINGLE)
       import_gauge_t<float, float>(this, U);
@@ -979,6 +998,13 @@ int cgptb_delete_fermion_operator(cgptb_fermion_operator* op) {
       if (op->links[p]) cudaFree(op->links[p]);
       if (op->clov[p]) cudaFree(op->clov[p]);
       if (op->clov_inv[p]) cudaFree(op->clov_inv[p]);
+    }
+    for (int mu = 0; mu < 4; mu++) {
+      for (int side = 0; side < 2; side++) {
+        if (op->halo_send[mu][side]) cudaFree(op->halo_send[mu][side]);
+        if (op->halo_recv[mu][side]) cudaFree(op->halo_recv[mu][side]);
+      }
+      if (op->ghost_links[mu]) cudaFree(op->ghost_links[mu]);
     }
     if (op->s_coef) cudaFree(op->s_coef);
     if (op->s_inv) cudaFree(op->s_inv);

@@ -27,6 +27,12 @@ struct cgptb_fermion_operator {
   void* s_inv = 0;              // dense MooeeInv blocks [P+, P-, P+^T, P-^T][Ls][Ls]
   cgptb_lattice* tmp_full[4] = {0, 0, 0, 0};
   cgptb_lattice* tmp_half[4] = {0, 0, 0, 0};
+  // multi-GPU decomposition (halo.cu); g.comm_mask marks the split directions
+  int goff[4] = {0, 0, 0, 0};   // global coordinate of the local origin
+  int gL[4] = {0, 0, 0, 0};     // global extents
+  void* halo_send[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};  // [mu][lo,hi] projected faces of one parity
+  void* halo_recv[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+  void* ghost_links[4] = {0, 0, 0, 0};  // U_mu on the high face of the rank-mu neighbour (double)
 
   int ls() const { return Ls > 0 ? Ls : 1; }
   void check_field(const cgptb_lattice* l) const;
@@ -42,4 +48,8 @@ void op_mooee(cgptb_fermion_operator* op, bool inverse, bool dag, bool acc, cons
 void op_s_tridiag(cgptb_fermion_operator* op, int kind, bool dag, bool acc, const cgptb_lattice* in, cgptb_lattice* out);
 void op_s_dense(cgptb_fermion_operator* op, bool dag, const cgptb_lattice* in, cgptb_lattice* out);
 void op_apply(cgptb_fermion_operator* op, int opcode, const cgptb_lattice* src, cgptb_lattice* dst);
+// halo.cu
+void halo_setup(cgptb_fermion_operator* op, const cgptb_lattice* const U[4]);
+void halo_begin(cgptb_fermion_operator* op, bool dag, int p_out, const void* in, size_t in_stride);
+void halo_end(cgptb_fermion_operator* op, bool dag, int p_out, void* out, size_t out_stride);
 }  // namespace cgptb

@@ -61,6 +61,10 @@ int cgptb_cg_eo2_ne(cgptb_fermion_operator* op, cgptb_lattice* psi, const cgptb_
   for (int i = 0; i < 4; i++)
     if (cgptb_create_lattice(all[i], op->dims4, op->Ls, op->prec, CGPTB_OT_VSPINCOLOR, src->cb)) CGPTB_ERR("%s", cgptb_last_error());
 
+  struct GlobalSums {  // reductions inside the solver are global sums (cg.py gets them via grid.globalsum)
+    GlobalSums() { g_reduce_global = true; }
+    ~GlobalSums() { g_reduce_global = false; }
+  } global_sums;
   auto mat = [&](cgptb_lattice* o, const cgptb_lattice* i) {
     op_schur_two(op, false, i, v);
     op_schur_two(op, true, v, o);

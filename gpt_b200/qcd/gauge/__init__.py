@@ -6,7 +6,7 @@ import gpt_b200 as g
 
 def unit(grid):
     U = []
-    n = grid.gsites
+    n = grid.lsites
     a = np.zeros((n, 3, 3), dtype=grid.precision.complex_dtype)
     a[:, range(3), range(3)] = 1.0
     for mu in range(4):
@@ -21,7 +21,7 @@ def from_numpy(grid, arrays):
     U = []
     for mu in range(4):
         u = g.mcolor(grid)
-        u[:] = np.asarray(arrays[mu]).reshape(grid.gsites, 3, 3)
+        u[:] = np.asarray(arrays[mu]).reshape(grid.lsites, 3, 3)
         U.append(u)
     return U
 

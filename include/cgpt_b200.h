@@ -60,6 +60,17 @@ int cgptb_device_info(int* sm_count, size_t* total_mem, int* cc_major, int* cc_m
 /* number of kernels this library has launched since init (for bench.py's gpu_launches) */
 uint64_t cgptb_launch_count(void);
 
+/* ---- processor grid (one process per GPU; GPT's --mpi X.Y.Z.T, lib/gpt/core/grid.py:77-94) ---------------- */
+/* rank 0 creates the 128-byte NCCL id, the host layer broadcasts it (torch.distributed / MPI), every rank then
+   calls cgptb_comm_init with the processor grid mpi = {1, Y, Z, T} (x cannot be split; s never is).  From then
+   on lattice extents passed to this library are LOCAL extents and fermion operators exchange halos.        */
+int cgptb_comm_unique_id(char* id128);
+int cgptb_comm_init(int rank, int world, const int mpi[4], const char* id128);
+int cgptb_comm_finalize(void);
+int cgptb_comm_info(int* rank, int* world, int pgrid[4], int pcoor[4]);
+/* cgpt.grid_globalsum (lib/cgpt/lib/grid.cc:119-160): in-place sum over ranks of n doubles in host memory */
+int cgptb_comm_globalsum(double* host, int n);
+
 /* ---- lattices (storage seam; cgpt.create_lattice & co., lib/cgpt/lib/lattice.cc:42-210) ----------- */
 /* dims4 = local x,y,z,t extents (all even); Ls = 0 for a 4d grid, else the extent of the 5th dimension
    (grid dimension 0, never checkerboarded: lib/gpt/core/grid.py:31-37); cb = CGPTB_EVEN/ODD for a field
