@@ -1,0 +1,99 @@
+"""
+CPU tests of the drop-in boundary and the host logic (no GPU needed):
+  * libcgpt_b200.so loads and exports every symbol include/cgpt_b200.h declares (no compute calls here);
+  * without a CUDA device the product path fails loudly instead of falling back to anything on the CPU;
+  * parameter handling mirrors the reference (@params_convention, opcode table);
+  * the processor-grid helpers of the multi-GPU path.
+"""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "cgpt_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(cgptb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gpt_b200 import cgpt
+
+    lib = ctypes.CDLL(cgpt.LIBRARY_PATH)
+    declared = _header_symbols()
+    assert len(declared) >= 45
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/cgpt_b200.h but not exported"
+    # the ctypes binding covers the same set
+    assert sorted(cgpt.SIGNATURES) == declared
+    cgpt.library()  # attaches the signatures
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    from gpt_b200 import cgpt
+
+    with pytest.raises(RuntimeError, match="no CUDA device|CUDA"):
+        cgpt.init(0)
+    import gpt_b200 as g
+
+    with pytest.raises(RuntimeError):
+        g.vspincolor(g.grid([4, 4, 4, 4], g.double))
+
+
+def test_product_never_imports_oracle():
+    for base, _, files in os.walk(os.path.join(ROOT, "gpt_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(base, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_params_convention():
+    import gpt_b200 as g
+
+    @g.params_convention(a=1, b=None)
+    def f(x, params):
+        return x, params
+
+    assert f(3, {"a": 2}) == (3, {"a": 2, "b": None})
+    assert f(3, b=5) == (3, {"a": 1, "b": 5})
+    assert f(3, {"a": 2}, a=7)[1]["a"] == 7
+    with pytest.raises(Exception):
+        f(3, c=1)
+
+
+def test_opcode_table_matches_reference_registry():
+    # lib/cgpt/lib/operators/register.h:2-20
+    from gpt_b200.qcd.fermion.register import OPCODES
+
+    ref = {"M": 2001, "Mdag": 2002, "Meooe": 2003, "MeooeDag": 2004, "Mooee": 2005, "MooeeDag": 2006, "MooeeInv": 2007,
+           "MooeeInvDag": 2008, "Mdiag": 2009, "Dminus": 2010, "DminusDag": 2011, "ImportPhysicalFermionSource": 2012,
+           "ImportUnphysicalFermion": 2013, "ExportPhysicalFermionSolution": 2014, "ExportPhysicalFermionSource": 2015,
+           "Dhop": 3001, "DhopDag": 4001, "DhopEO": 3002, "DhopEODag": 4002}
+    assert OPCODES == ref
+    header = open(os.path.join(ROOT, "include", "cgpt_b200.h")).read()
+    for name, code in ref.items():
+        assert re.search(rf"CGPTB_OP_{name}\s*=\s*{code}\b", header), name
+
+
+def test_processor_grid_helpers():
+    from gpt_b200 import parallel
+
+    assert parallel.default_mpi(1) == [1, 1, 1, 1]
+    assert parallel.default_mpi(2) == [1, 1, 1, 2]
+    assert parallel.default_mpi(4) == [1, 1, 1, 4]
+    assert parallel.default_mpi(8) == [1, 1, 2, 4]
+    assert parallel.local_dims([32, 32, 64, 256], [1, 1, 2, 4]) == [32, 32, 32, 64]
+    with pytest.raises(ValueError):
+        parallel.local_dims([8, 8, 8, 12], [1, 1, 1, 4])  # local extent 3 is odd
+    coords = [parallel.processor_coor(r, [1, 1, 2, 4]) for r in range(8)]
+    assert coords[0] == [0, 0, 0, 0] and coords[1] == [0, 0, 1, 0] and coords[2] == [0, 0, 0, 1] and coords[7] == [0, 0, 1, 3]
+    assert len({tuple(c) for c in coords}) == 8
