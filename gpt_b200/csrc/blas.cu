@@ -240,6 +240,31 @@ static void reduce_t(const cgptb_lattice* a, const cgptb_lattice* b, bool dot, b
   res[2] = h[2];
 }
 
+// per-CTA partial sums written by another kernel (e.g. the fused Dslash epilogue) -> host, fixed order
+static double* g_partial = 0;
+static size_t g_partial_n = 0;
+double* blas_partial_scratch(int nblocks) {
+  size_t n = (size_t)nblocks * 3 + 8;
+  if (n > g_partial_n) {
+    if (g_partial) CUDA_CHECK(cudaFree(g_partial));
+    CUDA_CHECK(cudaMalloc(&g_partial, n * sizeof(double)));
+    g_partial_n = n;
+  }
+  return g_partial;
+}
+
+void blas_finalize(int nblocks, int ncomp, const double* partial, double* host_out) {
+  CGPTB_ASSERT(ncomp <= 3);
+  double* out = const_cast<double*>(partial) + (size_t)nblocks * 3;
+  k_final<<<1, BT, 0, g_stream>>>(nblocks, ncomp, partial, out);
+  LAUNCH_CHECK();
+  if (g_reduce_global) comm_allreduce_device(out, ncomp, g_stream);
+  double* h = reduce_host(8);
+  CUDA_CHECK(cudaMemcpyAsync(h, out, ncomp * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  CUDA_CHECK(cudaStreamSynchronize(g_stream));
+  for (int i = 0; i < ncomp; i++) host_out[i] = h[i];
+}
+
 static void reduce_any(const cgptb_lattice* a, const cgptb_lattice* b, bool dot, bool nrm, double res[3]) {
   check_vec(a);
   if (b) CGPTB_ASSERT(same_shape(a, b));

