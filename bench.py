@@ -230,6 +230,32 @@ def run_native(args):
         e2e = {"value": FLOPS_PER_SITE * v5 * world / (ms_e / n_e2e * 1e-3) / 1e9, "unit": "GFlop/s",
                "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": n_e2e, "ms_per_step": ms_e / n_e2e}
 
+    # eo-CG time-to-solve (second half of BASELINE.json's metric): eo2_ne CG on the same operator and source,
+    # fixed iteration count so that the number is comparable across runs (single precision, device-side loop)
+    cg_info = None
+    if not args.no_cg:
+        half = g.vspincolor(qm.F_grid_eo)
+        g.pick_checkerboard(g.odd, half, src)
+        psi = g.lattice(half)
+        psi[:] = 0
+        cgpt.cg_eo2_ne(qm.interface.obj, psi.obj, half.obj, 1e-30, 3)  # warm-up
+        psi[:] = 0
+        sync()
+        l1 = cgpt.launch_count()
+        cgpt.timer_start()
+        hist, conv = cgpt.cg_eo2_ne(qm.interface.obj, psi.obj, half.obj, 1e-30, args.cg_iterations)
+        ms_cg = cgpt.timer_stop()
+        sync()
+        if dist is not None:
+            t = torch.tensor([ms_cg], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_cg = float(t.item())
+        cg_info = {"solver": "inv.preconditioned(pc.eo2_ne(), inv.cg) on Mpc^dag Mpc, fused device loop", "iterations": len(hist),
+                   "ms_total": ms_cg, "ms_per_iteration": ms_cg / max(len(hist), 1),
+                   "residual_reduction": (hist[-1] / hist[0]) ** 0.5 if hist else None,
+                   "launches_per_iteration": (cgpt.launch_count() - l1) / max(len(hist), 1)}
+        del half, psi
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(sample_dims=[16, 16, 16, 32], seconds=12.0)
@@ -246,7 +272,7 @@ def run_native(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "k_dhop_f32 (packed FFMA2 stencil, one launch per parity)", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_per_launch, "launches_per_step": launches_per_step},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "eo_cg": cg_info,
         }
         print(json.dumps(out))
     if dist is not None:
@@ -322,6 +348,8 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-cg", action="store_true")
+    ap.add_argument("--cg-iterations", type=int, default=50)
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

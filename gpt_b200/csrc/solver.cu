@@ -20,6 +20,8 @@ void dhop_half_f32_fused(cgptb_fermion_operator* op, bool dag, const float* pin,
                          int p_out, int sweep_mode, const float* z, size_t z_stride, const float* dotp, size_t dot_stride,
                          double* partial);
 bool sweep_supported(int ls);  // sweep.cu
+bool op_cg_update_sweep(cgptb_fermion_operator* op, double a, double b, cgptb_lattice* p, const cgptb_lattice* r, cgptb_lattice* psi,
+                        cgptb_lattice* t);
 void blas_finalize(int nblocks, int ncomp, const double* partial, double* host_out);  // blas.cu
 double* blas_partial_scratch(int nblocks);
 
@@ -33,8 +35,9 @@ static void fused_dhop(cgptb_fermion_operator* op, bool dag, const cgptb_lattice
 
 // o = i - Meooe MooeeInv Meooe MooeeInv i      (dag: o = i - MooeeInv^dag Meooe^dag MooeeInv^dag Meooe^dag i)
 // dot (optional, 3 doubles): re<dotp,o>, im<dotp,o>, |o|^2 (global sums inside the solver)
+// t_in (optional): T in, already computed by the fused CG update (non-dag only)
 void op_schur_two(cgptb_fermion_operator* op, bool dag, const cgptb_lattice* in, cgptb_lattice* out, const cgptb_lattice* dotp,
-                  double* dot) {
+                  double* dot, const cgptb_lattice* t_in = 0) {
   CGPTB_ASSERT(in->cb != CGPTB_FULL && in->data != out->data);
   op->check_field(in);
   op->check_field(out);
@@ -48,7 +51,10 @@ void op_schur_two(cgptb_fermion_operator* op, bool dag, const cgptb_lattice* in,
     if (dhop_fusable(op)) {
       double* partial = dot ? blas_partial_scratch(dhop_tile_blocks(op)) : 0;
       if (!dag) {
-        op_s_sweep(op, SWEEP_T, in, td);                                   // T x
+        if (t_in)
+          td = const_cast<cgptb_lattice*>(t_in);
+        else
+          op_s_sweep(op, SWEEP_T, in, td);                                 // T x
         fused_dhop(op, false, td, tc1, SWEEP_T, 0, 0, 0);                  // T Dhop (.)         D -> C
         fused_dhop(op, false, tc1, out, -1, in, dot ? dotp : 0, partial);  // x - Dhop (.)       C -> D
       } else {
@@ -103,7 +109,7 @@ extern "C" {
 
 int cgptb_apply_schur_two(cgptb_fermion_operator* op, int dag, const cgptb_lattice* in, cgptb_lattice* out) {
   CGPTB_API_BEGIN
-  op_schur_two(op, dag != 0, in, out, 0, 0);
+  op_schur_two(op, dag != 0, in, out, 0, 0, 0);
   CGPTB_API_END
 }
 
@@ -116,16 +122,18 @@ int cgptb_cg_eo2_ne(cgptb_fermion_operator* op, cgptb_lattice* psi, const cgptb_
   psi->cb = src->cb;
   *iterations = 0;
   *converged = 0;
-  cgptb_lattice *p = 0, *mmp = 0, *r = 0, *v = 0;
-  cgptb_lattice** all[4] = {&p, &mmp, &r, &v};
+  cgptb_lattice *p = 0, *mmp = 0, *r = 0, *v = 0, *tp = 0;
+  cgptb_lattice** all[5] = {&p, &mmp, &r, &v, &tp};
   struct Guard {
     cgptb_lattice*** a;
     ~Guard() {
-      for (int i = 0; i < 4; i++)
+      for (int i = 0; i < 5; i++)
         if (*a[i]) cgptb_delete_lattice(*a[i]);
     }
   } guard{all};
-  for (int i = 0; i < 4; i++)
+  static int no_upd = getenv("CGPTB_NO_FUSED_UPDATE") ? 1 : 0;
+  bool fuse_update = !no_upd && dhop_fusable(op) && sweep_supported(op->Ls);
+  for (int i = 0; i < (fuse_update ? 5 : 4); i++)
     if (cgptb_create_lattice(all[i], op->dims4, op->Ls, op->prec, CGPTB_OT_VSPINCOLOR, src->cb)) CGPTB_ERR("%s", cgptb_last_error());
 
   struct GlobalSums {  // reductions inside the solver are global sums (cg.py gets them via grid.globalsum)
@@ -133,9 +141,10 @@ int cgptb_cg_eo2_ne(cgptb_fermion_operator* op, cgptb_lattice* psi, const cgptb_
     ~GlobalSums() { g_reduce_global = false; }
   } global_sums;
   // o = Mpc^dag Mpc i ; d3 (optional) = <i, o> fused into the last kernel
+  bool have_tp = false;  // tp = T p from the fused update of the previous iteration
   auto mat = [&](cgptb_lattice* o, const cgptb_lattice* i, double* d3) {
-    op_schur_two(op, false, i, v, 0, 0);
-    op_schur_two(op, true, v, o, d3 ? i : 0, d3);
+    op_schur_two(op, false, i, v, 0, 0, (have_tp && i == p) ? tp : 0);
+    op_schur_two(op, true, v, o, d3 ? i : 0, d3, 0);
   };
   double n2;
   mat(mmp, psi, 0);
@@ -158,10 +167,15 @@ int cgptb_cg_eo2_ne(cgptb_fermion_operator* op, cgptb_lattice* psi, const cgptb_
     double a = c / d;
     if (cgptb_lattice_axpy_norm2(r, -a, 0.0, mmp, r, &cp)) CGPTB_ERR("%s", cgptb_last_error());
     double b = cp / c;
-    double ca[2] = {a, 0.0};
-    const cgptb_lattice* pp[1] = {p};
-    blas_lc(psi, 1, 1, ca, pp);  // psi += a p
-    blas_axpy(p, b, 0.0, p, r);  // p = b p + r
+    if (fuse_update && op_cg_update_sweep(op, a, b, p, r, psi, tp)) {
+      have_tp = true;  // psi += a p ; p = b p + r ; tp = T p in one pass
+    } else {
+      double ca[2] = {a, 0.0};
+      const cgptb_lattice* pp[1] = {p};
+      blas_lc(psi, 1, 1, ca, pp);  // psi += a p
+      blas_axpy(p, b, 0.0, p, r);  // p = b p + r
+      have_tp = false;
+    }
     double res = fabs(cp);
     if (history) history[k] = res;
     *iterations = k + 1;

@@ -7,6 +7,7 @@
 // Pure HBM streaming, so it is written as a persistent kernel: CTAs loop over tiles of NSB sites, tile i+1 is
 // fetched with cp.async (global -> shared, no register staging, s fastest = fully coalesced) while tile i is swept
 // in registers and written back.
+#include <string.h>
 #include "sweep.cuh"
 
 namespace cgptb {
@@ -16,9 +17,19 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
 }
 
-template <typename T, int LS, int NSB>
-__global__ void __launch_bounds__(NSB* VecOf<T>::NB) k_s_sweep(size_t n4, const T* __restrict__ in, T* __restrict__ out,
-                                                               size_t stride, SweepParams<T> P, int ntiles) {
+// CG vector update fused in front of the sweep (cg.py:91-95 + the first factor of the next matrix application):
+//   psi += a p ; p = b p + r ; out = T p         (in = p is updated in place)
+template <typename T>
+struct UpdateArgs {
+  T a, b;
+  const T* r;
+  T* psi;
+  T* p;
+};
+
+template <typename T, int LS, int NSB, bool UPD>
+__global__ void __launch_bounds__(NSB* VecOf<T>::NB, 2) k_s_sweep(size_t n4, const T* __restrict__ in, T* __restrict__ out,
+                                                               size_t stride, SweepParams<T> P, int ntiles, UpdateArgs<T> upd) {
   typedef typename VecOf<T>::type V;
   constexpr int NB = VecOf<T>::NB;
   constexpr int PITCH = LS + 1;  // vectors per (block, site) row in shared memory: conflict-free column reads
@@ -57,6 +68,48 @@ __global__ void __launch_bounds__(NSB* VecOf<T>::NB) k_s_sweep(size_t n4, const 
     __syncthreads();
     size_t site0 = (size_t)tile * NSB;
     int nloc = (int)((n4 - site0) < (size_t)NSB ? (n4 - site0) : NSB);
+    if (UPD) {
+      const V* gr = reinterpret_cast<const V*>(upd.r);
+      V* gpsi = reinterpret_cast<V*>(upd.psi);
+      V* gp = reinterpret_cast<V*>(upd.p);
+      constexpr int CH = 4;  // loads in flight per thread and field: CH x 16 bytes
+#pragma unroll
+      for (int it0 = 0; it0 < LS; it0 += CH) {
+        V rv[CH], sv[CH];
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+          int it = it0 + c;
+          if (it < LS) {
+            int idx = threadIdx.x + it * NT;
+            int k = idx / (NSB * LS), rem = idx - k * (NSB * LS);
+            int l = rem / LS;
+            if (l < nloc) {
+              size_t o = (size_t)k * stride + site0 * LS + rem;
+              rv[c] = __ldcs(gr + o);
+              sv[c] = __ldcs(gpsi + o);
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+          int it = it0 + c;
+          if (it < LS) {
+            int idx = threadIdx.x + it * NT;
+            int k = idx / (NSB * LS), rem = idx - k * (NSB * LS);
+            int l = rem / LS, s = rem - l * LS;
+            if (l < nloc) {
+              size_t o = (size_t)k * stride + site0 * LS + rem;
+              V pv = buf[(k * NSB + l) * PITCH + s];
+              __stcs(gpsi + o, vfma(upd.a, pv, sv[c]));
+              V pn = vfma(upd.b, pv, rv[c]);
+              __stcs(gp + o, pn);
+              buf[(k * NSB + l) * PITCH + s] = pn;
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
     {
       int l = threadIdx.x % NSB, k = threadIdx.x / NSB;
       if (l < nloc) sweep_row<T, LS>(P, k, buf + (k * NSB + l) * PITCH);
@@ -81,13 +134,13 @@ constexpr int sweep_nsb() {
   return n;
 }
 
-template <typename T, int LS>
-static void launch_sweep(size_t n4, const T* in, T* out, size_t stride, const SweepParams<T>& P) {
+template <typename T, int LS, bool UPD>
+static void launch_sweep(size_t n4, const T* in, T* out, size_t stride, const SweepParams<T>& P, const UpdateArgs<T>& upd) {
   constexpr int NSB = sweep_nsb<T, LS>();
   constexpr size_t smem = (size_t)2 * VecOf<T>::NB * NSB * (LS + 1) * 16;
   static bool configured = false;
   if (!configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(k_s_sweep<T, LS, NSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_CHECK(cudaFuncSetAttribute(k_s_sweep<T, LS, NSB, UPD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   int ntiles = (int)((n4 + NSB - 1) / NSB);
@@ -96,7 +149,21 @@ static void launch_sweep(size_t n4, const T* in, T* out, size_t stride, const Sw
   if (per_sm > 4) per_sm = 4;
   int blocks = sm_count() * per_sm;
   if (blocks > ntiles) blocks = ntiles;
-  k_s_sweep<T, LS, NSB><<<blocks, NSB * VecOf<T>::NB, smem, g_stream>>>(n4, in, out, stride, P, ntiles);
+  k_s_sweep<T, LS, NSB, UPD><<<blocks, NSB * VecOf<T>::NB, smem, g_stream>>>(n4, in, out, stride, P, ntiles, upd);
+}
+
+template <typename T, bool UPD>
+static bool launch_sweep_ls(int ls, size_t n4, const T* in, T* out, size_t stride, const SweepParams<T>& P, const UpdateArgs<T>& upd) {
+  switch (ls) {
+    case 4: launch_sweep<T, 4, UPD>(n4, in, out, stride, P, upd); break;
+    case 6: launch_sweep<T, 6, UPD>(n4, in, out, stride, P, upd); break;
+    case 8: launch_sweep<T, 8, UPD>(n4, in, out, stride, P, upd); break;
+    case 12: launch_sweep<T, 12, UPD>(n4, in, out, stride, P, upd); break;
+    case 16: launch_sweep<T, 16, UPD>(n4, in, out, stride, P, upd); break;
+    case 24: launch_sweep<T, 24, UPD>(n4, in, out, stride, P, upd); break;
+    default: return false;
+  }
+  return true;
 }
 
 template <typename T>
@@ -107,17 +174,37 @@ static bool sweep_t(cgptb_fermion_operator* op, int mode, const cgptb_lattice* i
   size_t n4 = in->sites / ls;
   const T* pin = (const T*)in->data;
   T* pout = (T*)out->data;
-  switch (ls) {
-    case 4: launch_sweep<T, 4>(n4, pin, pout, in->sites, P); break;
-    case 6: launch_sweep<T, 6>(n4, pin, pout, in->sites, P); break;
-    case 8: launch_sweep<T, 8>(n4, pin, pout, in->sites, P); break;
-    case 12: launch_sweep<T, 12>(n4, pin, pout, in->sites, P); break;
-    case 16: launch_sweep<T, 16>(n4, pin, pout, in->sites, P); break;
-    case 24: launch_sweep<T, 24>(n4, pin, pout, in->sites, P); break;
-    default: return false;
-  }
+  UpdateArgs<T> none;
+  memset(&none, 0, sizeof(none));
+  if (!launch_sweep_ls<T, false>(ls, n4, pin, pout, in->sites, P, none)) return false;
   LAUNCH_CHECK();
   return true;
+}
+
+// psi += a p ; p = b p + r ; t = T p   in one pass (CG update + first factor of the next Mpc)
+template <typename T>
+static bool cg_update_t(cgptb_fermion_operator* op, double a, double b, cgptb_lattice* p, const cgptb_lattice* r, cgptb_lattice* psi,
+                        cgptb_lattice* t) {
+  SweepParams<T> P;
+  if (!make_sweep_params<T>(op, SWEEP_T, P)) return false;
+  UpdateArgs<T> upd;
+  upd.a = (T)a;
+  upd.b = (T)b;
+  upd.r = (const T*)r->data;
+  upd.psi = (T*)psi->data;
+  upd.p = (T*)p->data;
+  if (!launch_sweep_ls<T, true>(op->Ls, p->sites / op->Ls, (const T*)p->data, (T*)t->data, p->sites, P, upd)) return false;
+  LAUNCH_CHECK();
+  return true;
+}
+
+bool op_cg_update_sweep(cgptb_fermion_operator* op, double a, double b, cgptb_lattice* p, const cgptb_lattice* r, cgptb_lattice* psi,
+                        cgptb_lattice* t) {
+  if (op->type != CGPTB_MOBIUS || !(op->Ls == 4 || op->Ls == 6 || op->Ls == 8 || op->Ls == 12 || op->Ls == 16 || op->Ls == 24)) return false;
+  CGPTB_ASSERT(same_shape(p, r) && same_shape(p, psi) && same_shape(p, t));
+  bool ok = op->prec == CGPTB_SINGLE ? cg_update_t<float>(op, a, b, p, r, psi, t) : cg_update_t<double>(op, a, b, p, r, psi, t);
+  if (ok) t->cb = p->cb;
+  return ok;
 }
 
 bool sweep_supported(int ls) { return ls == 4 || ls == 6 || ls == 8 || ls == 12 || ls == 16 || ls == 24; }

@@ -119,3 +119,29 @@ def test_oracle_structure(fingerprint_fields):
     full = m.M(se)
     assert np.linalg.norm(e.proj(full, 1) - e.Meooe(se, 0)) / np.linalg.norm(full) < 1e-13
     assert np.linalg.norm(e.proj(full, 0) - e.Mooee(se)) / np.linalg.norm(full) < 1e-13
+
+
+PION_REF = [
+    1.0710210800170898, 0.08988216519355774, 0.015699388459324837, 0.003721018321812153, 0.0010877142194658518,
+    0.0003579717595130205, 0.00012700144725386053, 5.180457083042711e-05, 3.406393443583511e-05, 5.2738148951902986e-05,
+    0.0001297977869398892, 0.0003634534077718854, 0.0011047901352867484, 0.0037904218770563602, 0.015902264043688774,
+    0.09077762067317963,
+]
+PION_PARAMS = dict(kappa=0.137, csw_r=0.0, csw_t=0.0, xi_0=1.0, nu=1.0, isAnisotropic=False,
+                   boundary_phases=[np.exp(1j), np.exp(2j), np.exp(3j), np.exp(4j)])
+
+
+def test_wilson_pion_correlator_golden():
+    """end-to-end pin: eo2_ne CG Wilson propagator from a point source at [1,0,0,0] and its pion correlator
+    (/root/reference/tests/qcd/fermion_operators.py:12-43,135-218; 16 values, tolerance 1e-5)"""
+    dims = [8, 8, 8, 16]
+    rng = random("test")
+    U = qcd.gauge_random(rng, dims)
+    w = qcd.wilson_clover(U, **PION_PARAMS)
+    corr = np.zeros(16)
+    for col in range(12):
+        src = np.zeros(tuple(dims[::-1]) + (4, 3), dtype=np.complex128)
+        src[0, 0, 0, 1].reshape(12)[col] = 1.0  # [t,z,y,x] = point (x=1, y=z=t=0)
+        sol, hist = qcd.propagator_column(w, src, 1e-6, 1000)
+        corr += np.sum(np.abs(sol) ** 2, axis=(1, 2, 3, 4, 5))
+    assert np.linalg.norm(corr - np.array(PION_REF)) < 1e-5
