@@ -147,6 +147,7 @@ struct TileGeom {
   int nxh, ny, nz, nt;   // tiles per dimension
   int zslab;             // z-tiles per slab
   int stream_stores;     // write the output with st.global.cs
+  const int2* zt_table;  // blockIdx.z -> (z tile, t tile), slab order (device memory)
 };
 
 static const int LINK_F4 = 37;  // float4 per site in shared memory: 36 (8 links x 72 B) + 1 pad -> 148 words, bank shift 20
@@ -225,28 +226,17 @@ __global__ void __launch_bounds__(NS* LS / SPER, MINB)
   constexpr int NT = NS * LS / SPER;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* slinks = reinterpret_cast<float4*>(smem_raw);  // [NS][LINK_F4]
-  // tile coordinates: x fastest, then y, z inside the slab, t, slab (the last slab may be narrower)
-  int b = blockIdx.x;
-  int bx = b % tg.nxh;
-  b /= tg.nxh;
-  int by = b % tg.ny;
-  b /= tg.ny;
-  int per_slab = tg.zslab * tg.nt;
-  int slab = b / per_slab;
-  int slab0 = slab * tg.zslab;
-  int zw = tg.zslab;
-  if (slab0 + zw > tg.nz) zw = tg.nz - slab0;
-  b -= slab * per_slab;
-  int bz = slab0 + b % zw;
-  int bt = b / zw;
+  // tile coordinates: grid = (x tiles, y tiles, (z in slab, t, slab)); the last index is decoded with a small table so
+  // that no thread executes an integer division by a run-time value
+  constexpr int TXH = NS == 32 ? 4 : 2, TY = 2, TZ = 2;  // tile = TXH x 2 x 2 x 2 checkerboard sites
+  const int bx = blockIdx.x, by = blockIdx.y;
+  const int2 zt = tg.zt_table[blockIdx.z];
+  const int bz = zt.x, bt = zt.y;
 
   const int l = threadIdx.x / TPS;
   const int j = threadIdx.x - l * TPS;
-  int lx = l % tg.txh, r0 = l / tg.txh;
-  int ly = r0 % tg.ty;
-  r0 /= tg.ty;
-  int lz = r0 % tg.tz, lt = r0 / tg.tz;
-  const int xh = bx * tg.txh + lx, y = by * tg.ty + ly, z = bz * tg.tz + lz, t = bt * tg.tt + lt;
+  const int lx = l % TXH, ly = (l / TXH) % TY, lz = (l / (TXH * TY)) % TZ, lt = l / (TXH * TY * TZ);
+  const int xh = bx * TXH + lx, y = by * TY + ly, z = bz * TZ + lz, t = bt * 2 + lt;
   const int i4 = xh + g.hx * (y + g.L[1] * (z + g.L[2] * t));
   const int x = 2 * xh + ((y + z + t + p_out) & 1);
 
@@ -254,9 +244,16 @@ __global__ void __launch_bounds__(NS* LS / SPER, MINB)
   {
     const float4* gl = reinterpret_cast<const float4*>(links) + (size_t)i4 * 36;
     unsigned sbase = (unsigned)__cvta_generic_to_shared(slinks + l * LINK_F4);
+    if (36 % TPS == 0) {
 #pragma unroll
-    for (int m = j; m < 36; m += TPS)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + m * 16), "l"(gl + m));
+      for (int i = 0; i < 36 / TPS; i++) {
+        int m = j + i * TPS;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + m * 16), "l"(gl + m));
+      }
+    } else {
+      for (int m = j; m < 36; m += TPS)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + m * 16), "l"(gl + m));
+    }
     asm volatile("cp.async.commit_group;");
   }
   c32 acc[SPER][12];
@@ -336,9 +333,10 @@ __global__ void __launch_bounds__(NS* LS / SPER, MINB)
       __shared__ double red[96];
       block_reduce<3>(v, red);
       if (threadIdx.x == 0) {
-        epi.partial[blockIdx.x * 3 + 0] = v[0];
-        epi.partial[blockIdx.x * 3 + 1] = v[1];
-        epi.partial[blockIdx.x * 3 + 2] = v[2];
+        size_t cta = blockIdx.x + (size_t)gridDim.x * (blockIdx.y + (size_t)gridDim.y * blockIdx.z);
+        epi.partial[cta * 3 + 0] = v[0];
+        epi.partial[cta * 3 + 1] = v[1];
+        epi.partial[cta * 3 + 2] = v[2];
       }
     }
   }
@@ -367,38 +365,55 @@ static void launch_linear(int ls, unsigned blocks, int threads, const Geom& g, i
   }
 }
 
-// tile of NS checkerboard sites; returns false if the lattice is not divisible
+// tile of NS checkerboard sites (NS = 32: 4 x 2 x 2 x 2 in xh,y,z,t ; NS = 16: 2 x 2 x 2 x 2); returns false if the
+// lattice is not divisible.  The (z,t) tile order table is cached per geometry.
 static bool make_tiles(const Geom& g, int ns, TileGeom& tg) {
-  // NS = 32: 4 x 2 x 2 x 2 (xh,y,z,t) ; NS = 16: 2 x 2 x 2 x 2 ; NS = 8: 1 x 2 x 2 x 2
-  static const char* tile_env = getenv("CGPTB_TILE");
-  int e[4];
-  if (tile_env && sscanf(tile_env, "%d,%d,%d,%d", &e[0], &e[1], &e[2], &e[3]) == 4 && e[0] * e[1] * e[2] * e[3] == ns) {
-    tg.txh = e[0]; tg.ty = e[1]; tg.tz = e[2]; tg.tt = e[3];
-  } else if (ns == 32) {
-    tg.txh = 4; tg.ty = 2; tg.tz = 2; tg.tt = 2;
-  } else if (ns == 16) {
-    tg.txh = 2; tg.ty = 2; tg.tz = 2; tg.tt = 2;
-  } else {
-    tg.txh = 1; tg.ty = 2; tg.tz = 2; tg.tt = 2;
-  }
+  tg.txh = ns == 32 ? 4 : 2;
+  tg.ty = 2;
+  tg.tz = 2;
+  tg.tt = 2;
+  if (ns != 32 && ns != 16) return false;
   if (g.hx % tg.txh || g.L[1] % tg.ty || g.L[2] % tg.tz || g.L[3] % tg.tt) return false;
   tg.nxh = g.hx / tg.txh;
   tg.ny = g.L[1] / tg.ty;
   tg.nz = g.L[2] / tg.tz;
   tg.nt = g.L[3] / tg.tt;
+  if (tg.ny > 65535 || tg.nz * tg.nt > 65535) return false;
   static int zslab_sites = env_int("CGPTB_ZSLAB", 16);  // slab width in z (sites)
   static int stcs = env_int("CGPTB_STCS", 1);
   tg.stream_stores = stcs;
   tg.zslab = zslab_sites / tg.tz;
   if (tg.zslab < 1) tg.zslab = 1;
   if (tg.zslab > tg.nz) tg.zslab = tg.nz;
+  // order: z inside the slab fastest, then t, then the slab
+  struct Cache {
+    int nz, nt, zslab;
+    int2* dev;
+  };
+  static std::vector<Cache> cache;
+  for (auto& c : cache)
+    if (c.nz == tg.nz && c.nt == tg.nt && c.zslab == tg.zslab) {
+      tg.zt_table = c.dev;
+      return true;
+    }
+  std::vector<int2> h;
+  for (int slab0 = 0; slab0 < tg.nz; slab0 += tg.zslab) {
+    int zw = slab0 + tg.zslab > tg.nz ? tg.nz - slab0 : tg.zslab;
+    for (int t = 0; t < tg.nt; t++)
+      for (int zi = 0; zi < zw; zi++) h.push_back(make_int2(slab0 + zi, t));
+  }
+  int2* dev;
+  CUDA_CHECK(cudaMalloc(&dev, h.size() * sizeof(int2)));
+  CUDA_CHECK(cudaMemcpy(dev, h.data(), h.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  cache.push_back({tg.nz, tg.nt, tg.zslab, dev});
+  tg.zt_table = dev;
   return true;
 }
 
 template <bool DAG, int LS, int SPER, int NS, int MINB, int ABL, bool EPI>
 static void launch_tile_k(const Geom& g, const TileGeom& tg, int p_out, const float* in, size_t is, float* out, size_t os,
                           const float* links, const EpiArgs& epi) {
-  unsigned blocks = (unsigned)(tg.nxh * tg.ny * tg.nz * tg.nt);
+  dim3 blocks(tg.nxh, tg.ny, tg.nz * tg.nt);
   size_t smem = (size_t)NS * LINK_F4 * 16 + (EPI ? (size_t)6 * NS * (LS + 1) * 16 : 0);
   auto kern = k_dhop_f32_tile<DAG, LS, SPER, NS, MINB, ABL, EPI>;
   static bool configured = false;
