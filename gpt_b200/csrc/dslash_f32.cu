@@ -452,8 +452,8 @@ static bool launch_tiled(int ls, const Geom& g, int p_out, const float* in, size
   switch (ls) {
     case 8: return launch_tile_t<DAG, 8, 1, 32, 2>(g, p_out, in, is, out, os, links, epi);
     case 12:
-      if (variant == 7 && !epi) return launch_tile_t<DAG, 12, 2, 32, 2>(g, p_out, in, is, out, os, links, epi);
-      if (variant == 3 && !epi) return launch_tile_t<DAG, 12, 3, 32, 2>(g, p_out, in, is, out, os, links, epi);
+      if (variant == 7 && !epi) return launch_tile_t<DAG, 12, 1, 16, 4>(g, p_out, in, is, out, os, links, epi);
+      if (variant == 3 && !epi) return launch_tile_t<DAG, 12, 1, 16, 5>(g, p_out, in, is, out, os, links, epi);
       return launch_tile_t<DAG, 12, 1, 32, 2>(g, p_out, in, is, out, os, links, epi);
     case 16: return launch_tile_t<DAG, 16, 1, 16, 2>(g, p_out, in, is, out, os, links, epi);
     case 24: return launch_tile_t<DAG, 24, 1, 16, 2>(g, p_out, in, is, out, os, links, epi);
