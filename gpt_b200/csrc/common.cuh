@@ -5,10 +5,12 @@
 //     Within a half the 4d sites are in checkerboard order i4 = (x/2) + Lx/2*(y + Ly*(z + Lz*t)); a 5d
 //     field has the s index fastest: site = i4*Ls + s (Grid's order, evidence:
 //     lib/cgpt/lib/foundation/mobius_with_vector_field.h:79-81).
-//   * site-major SoA in 16-byte vector blocks: element block k of site i lives at data16[k*nsites + i].
-//     fp64: one complex per block (12 blocks per spinor); fp32 spinor: two complex per block (6 blocks);
-//     other fp32 objects (links, singlets): one complex (8 bytes) per block.
-//     A warp reading block k of 32 consecutive sites issues one fully coalesced 512-byte request.
+//   * site-major SoA in 32-byte vector blocks for spin-colour vectors: block k of site i lives at
+//     data32[k*nsites + i]; fp32 spinor = 3 blocks of 4 complex, fp64 spinor = 6 blocks of 2 complex.  One
+//     LDG.E.ENL2.256 (ld.global.v8.f32 / v4.f64, sm_100) moves a block, so a neighbour spinor costs 3 (fp32) or
+//     6 (fp64) load instructions and address computations instead of 6 / 12 with 16-byte blocks, and a warp
+//     reading block k of 32 consecutive sites issues one fully coalesced 1 KB request.
+//     Other objects (links, singlets): one complex per block ([component][site]).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -99,7 +101,9 @@ struct cgptb_lattice {
   size_t bytes() const { return nreals() * real_size(); }
   size_t half4() const { return (size_t)dims4[0] * dims4[1] * dims4[2] * dims4[3] / 2; }
   // complex components per 16-byte (or 8-byte) block
-  int cpb() const { return (prec == CGPTB_SINGLE && otype % 2 == 0) ? 2 : 1; }
+  int cpb() const { return otype % 4 == 0 ? (prec == CGPTB_SINGLE ? 4 : 2) : 1; }
+  // bytes of one vector block
+  size_t block_bytes() const { return (size_t)cpb() * 2 * real_size(); }
 };
 
 namespace cgptb {
@@ -121,36 +125,94 @@ struct vec_of<double> {
   typedef double2 type;
 };
 
+// ---- 256-bit global accesses (sm_100: LDG.E.ENL2.256 / STG.E.ENL2.256) ------------------------------------
+__device__ __forceinline__ void ld256(const float* p, float (&v)[8]) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void ld256(const double* p, double (&v)[4]) {
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+// coherent variant for fields that are read and written by the same kernel
+__device__ __forceinline__ void ld256_rw(const float* p, float (&v)[8]) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void ld256_rw(const double* p, double (&v)[4]) {
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void st256(float* p, const float (&v)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void st256(double* p, const double (&v)[4]) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+}
+__device__ __forceinline__ void st256_cs(float* p, const float (&v)[8]) {
+  asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+
 // ---- spinor accessors (24 reals: index (spin*3+color)*2 + reim) -----------------------------------
+// base: first block of the (half) field, nsites: sites per component plane, site: index within the plane
 __device__ __forceinline__ void load_spinor(const float* __restrict__ base, size_t nsites, size_t site, float (&p)[24]) {
-  const float4* b = reinterpret_cast<const float4*>(base);
 #pragma unroll
-  for (int k = 0; k < 6; k++) {
-    float4 v = __ldg(b + k * nsites + site);
-    p[4 * k + 0] = v.x;
-    p[4 * k + 1] = v.y;
-    p[4 * k + 2] = v.z;
-    p[4 * k + 3] = v.w;
+  for (int k = 0; k < 3; k++) {
+    float v[8];
+    ld256(base + (k * nsites + site) * 8, v);
+#pragma unroll
+    for (int e = 0; e < 8; e++) p[8 * k + e] = v[e];
   }
 }
 __device__ __forceinline__ void load_spinor(const double* __restrict__ base, size_t nsites, size_t site, double (&p)[24]) {
-  const double2* b = reinterpret_cast<const double2*>(base);
 #pragma unroll
-  for (int k = 0; k < 12; k++) {
-    double2 v = __ldg(b + k * nsites + site);
-    p[2 * k + 0] = v.x;
-    p[2 * k + 1] = v.y;
+  for (int k = 0; k < 6; k++) {
+    double v[4];
+    ld256(base + (k * nsites + site) * 4, v);
+#pragma unroll
+    for (int e = 0; e < 4; e++) p[4 * k + e] = v[e];
+  }
+}
+// same, for a field the kernel also writes (no read-only path)
+__device__ __forceinline__ void load_spinor_rw(const float* base, size_t nsites, size_t site, float (&p)[24]) {
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    float v[8];
+    ld256_rw(base + (k * nsites + site) * 8, v);
+#pragma unroll
+    for (int e = 0; e < 8; e++) p[8 * k + e] = v[e];
+  }
+}
+__device__ __forceinline__ void load_spinor_rw(const double* base, size_t nsites, size_t site, double (&p)[24]) {
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    double v[4];
+    ld256_rw(base + (k * nsites + site) * 4, v);
+#pragma unroll
+    for (int e = 0; e < 4; e++) p[4 * k + e] = v[e];
   }
 }
 __device__ __forceinline__ void store_spinor(float* __restrict__ base, size_t nsites, size_t site, const float (&p)[24]) {
-  float4* b = reinterpret_cast<float4*>(base);
 #pragma unroll
-  for (int k = 0; k < 6; k++) b[k * nsites + site] = make_float4(p[4 * k], p[4 * k + 1], p[4 * k + 2], p[4 * k + 3]);
+  for (int k = 0; k < 3; k++) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) v[e] = p[8 * k + e];
+    st256(base + (k * nsites + site) * 8, v);
+  }
 }
 __device__ __forceinline__ void store_spinor(double* __restrict__ base, size_t nsites, size_t site, const double (&p)[24]) {
-  double2* b = reinterpret_cast<double2*>(base);
 #pragma unroll
-  for (int k = 0; k < 12; k++) b[k * nsites + site] = make_double2(p[2 * k], p[2 * k + 1]);
+  for (int k = 0; k < 6; k++) {
+    double v[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) v[e] = p[4 * k + e];
+    st256(base + (k * nsites + site) * 4, v);
+  }
 }
 
 // generic complex-element accessor for any object type (used by import/export and setup kernels)

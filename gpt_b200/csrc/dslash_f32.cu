@@ -30,28 +30,28 @@ static int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
+// a spinor is 3 blocks of 32 bytes (4 complex each): 3 x LDG.E.ENL2.256 per neighbour
 __device__ __forceinline__ void load_spinor_c32(const float* __restrict__ base, size_t nsites, size_t site, c32 (&p)[12]) {
-  const float4* b = reinterpret_cast<const float4*>(base);
 #pragma unroll
-  for (int k = 0; k < 6; k++) {
-    float4 v = __ldg(b + k * nsites + site);
-    p[2 * k] = pk(v.x, v.y);
-    p[2 * k + 1] = pk(v.z, v.w);
+  for (int k = 0; k < 3; k++) {
+    float v[8];
+    ld256(base + (k * nsites + site) * 8, v);
+#pragma unroll
+    for (int e = 0; e < 4; e++) p[4 * k + e] = pk(v[2 * e], v[2 * e + 1]);
   }
 }
 
 template <bool STREAM>
 __device__ __forceinline__ void store_spinor_c32(float* __restrict__ base, size_t nsites, size_t site, const c32 (&p)[12]) {
-  float4* b = reinterpret_cast<float4*>(base);
 #pragma unroll
-  for (int k = 0; k < 6; k++) {
-    float4 v;
-    upk(p[2 * k], v.x, v.y);
-    upk(p[2 * k + 1], v.z, v.w);
+  for (int k = 0; k < 3; k++) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 4; e++) upk(p[4 * k + e], v[2 * e], v[2 * e + 1]);
     if (STREAM)
-      __stcs(b + k * nsites + site, v);
+      st256_cs(base + (k * nsites + site) * 8, v);
     else
-      b[k * nsites + site] = v;
+      st256(base + (k * nsites + site) * 8, v);
   }
 }
 

@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(128) k_exterior(Geom g, FaceGeom fg, int ls, i
   int x, y, z, t;
   int i4 = face_site(g, fg, p_out, side ? g.L[MU] - 1 : 0, f, x, y, z, t);
   T h[12], chi[12], W[18], acc[24];
-  load_spinor(out, out_stride, (size_t)i4 * ls + s, acc);
+  load_spinor_rw(out, out_stride, (size_t)i4 * ls + s, acc);
   if (side == 1) {  // forward neighbour lives on rank+mu
     HS<T>::load(from_hi, nface, idx, h);
     load_link<T>(links, (size_t)i4, MU, W);

@@ -238,7 +238,7 @@ int cgptb_create_lattice_view(cgptb_lattice** out, const int dims4[4], int Ls, i
                               void* device_ptr) {
   CGPTB_API_BEGIN
   CGPTB_ASSERT(device_ptr != 0);
-  CGPTB_ASSERT(((uintptr_t)device_ptr & 15) == 0);
+  CGPTB_ASSERT(((uintptr_t)device_ptr & 31) == 0);
   new_lattice(out, dims4, Ls, precision, otype, cb, device_ptr);
   CGPTB_API_END
 }

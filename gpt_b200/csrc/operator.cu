@@ -98,7 +98,7 @@ static void dhop_half(cgptb_fermion_operator* op, bool dag, const cgptb_lattice*
   size_t half = (size_t)op->g.half4 * ls;
   const T* pin = (const T*)in->data;
   T* pout = (T*)out->data;
-  const size_t blk_reals = 16 / sizeof(T);
+  const size_t blk_reals = 32 / sizeof(T);
   if (in->cb == CGPTB_FULL) pin += (size_t)(1 - p_out) * half * blk_reals;
   if (out->cb == CGPTB_FULL) pout += (size_t)p_out * half * blk_reals;
   // split lattice: faces go out first, the interior stencil hides the transfer, then the boundary update
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(128) k_s_tridiag(size_t n, int ls, const T* __
   load_spinor(in, stride, i4 * ls + sm, a);
   load_spinor(in, stride, i4 * ls + sp, b);
   T d = coef[s], lp = coef[ls + s], up = coef[2 * ls + s], lm = coef[3 * ls + s], um = coef[4 * ls + s];
-  if (ACC) load_spinor(out, stride, tid, r);
+  if (ACC) load_spinor_rw(out, stride, tid, r);
 #pragma unroll
   for (int k = 0; k < 12; k++) {
     T v = d * c[k] + lp * a[k] + up * b[k];
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(128) k_clover_apply(size_t n, const T* __restr
   if (i >= n) return;
   T psi[24], r[24];
   load_spinor(in, in_stride, i, psi);
-  if (ACC) load_spinor(out, out_stride, i, r);
+  if (ACC) load_spinor_rw(out, out_stride, i, r);
 #pragma unroll
   for (int blk = 0; blk < 2; blk++) {
     T o[12];
@@ -760,15 +760,15 @@ static void clover_apply(cgptb_fermion_operator* op, bool inverse, bool acc, con
     size_t off = in->cb == CGPTB_FULL ? (size_t)p * half : 0;
     void* cl = inverse ? op->clov_inv[p] : op->clov[p];
     if (op->prec == CGPTB_SINGLE) {
-      const float* pin = (const float*)in->data + off * 4;
-      float* pout = (float*)out->data + off * 4;
+      const float* pin = (const float*)in->data + off * 8;
+      float* pout = (float*)out->data + off * 8;
       if (acc)
         k_clover_apply<float, true><<<blocks, threads, 0, g_stream>>>(half, pin, in->sites, pout, out->sites, (const float*)cl);
       else
         k_clover_apply<float, false><<<blocks, threads, 0, g_stream>>>(half, pin, in->sites, pout, out->sites, (const float*)cl);
     } else {
-      const double* pin = (const double*)in->data + off * 2;
-      double* pout = (double*)out->data + off * 2;
+      const double* pin = (const double*)in->data + off * 4;
+      double* pout = (double*)out->data + off * 4;
       if (acc)
         k_clover_apply<double, true><<<blocks, threads, 0, g_stream>>>(half, pin, in->sites, pout, out->sites, (const double*)cl);
       else

@@ -1,6 +1,7 @@
 // Stand-alone fifth-dimension sweep kernel (see sweep.cuh for the algebra).
 //
-// One thread owns one 16-byte component block of one 4d site for ALL s (Ls values in registers) and runs a short
+// Spinor fields are stored in 32-byte blocks (common.cuh); a 16-byte "unit" k is half `k & 1` of block `k >> 1`.
+// One thread owns one 16-byte unit of one 4d site for ALL s (Ls values in registers) and runs a short
 // chain of stages, e.g. T = (b + c S5)(bee - cee S5)^-1 = "Meooe5D o MooeeInv" in a single pass over the field:
 // 48 reals of traffic per site instead of 96 (+ the dense Ls x Ls product) of the unfused kernels.
 //
@@ -46,9 +47,11 @@ __global__ void __launch_bounds__(NSB* VecOf<T>::NB, 2) k_s_sweep(size_t n4, con
 #pragma unroll
     for (int it = 0; it < LS; it++) {
       int idx = threadIdx.x + it * NT;
-      int k = idx / (NSB * LS), rem = idx - k * (NSB * LS);
+      int half = idx & 1, q = idx >> 1;
+      int kb = q / (NSB * LS), rem = q - kb * (NSB * LS);
+      int k = 2 * kb + half;
       int l = rem / LS, s = rem - l * LS;
-      if (l < nloc) cp_async16(buf + (k * NSB + l) * PITCH + s, gin + (size_t)k * stride + site0 * LS + rem);
+      if (l < nloc) cp_async16(buf + (k * NSB + l) * PITCH + s, gin + (((size_t)kb * stride + site0 * LS + rem) << 1) + half);
     }
     asm volatile("cp.async.commit_group;");
   };
@@ -81,10 +84,11 @@ __global__ void __launch_bounds__(NSB* VecOf<T>::NB, 2) k_s_sweep(size_t n4, con
           int it = it0 + c;
           if (it < LS) {
             int idx = threadIdx.x + it * NT;
-            int k = idx / (NSB * LS), rem = idx - k * (NSB * LS);
+            int half = idx & 1, q = idx >> 1;
+            int kb = q / (NSB * LS), rem = q - kb * (NSB * LS);
             int l = rem / LS;
             if (l < nloc) {
-              size_t o = (size_t)k * stride + site0 * LS + rem;
+              size_t o = (((size_t)kb * stride + site0 * LS + rem) << 1) + half;
               rv[c] = __ldcs(gr + o);
               sv[c] = __ldcs(gpsi + o);
             }
@@ -95,10 +99,12 @@ __global__ void __launch_bounds__(NSB* VecOf<T>::NB, 2) k_s_sweep(size_t n4, con
           int it = it0 + c;
           if (it < LS) {
             int idx = threadIdx.x + it * NT;
-            int k = idx / (NSB * LS), rem = idx - k * (NSB * LS);
+            int half = idx & 1, q = idx >> 1;
+            int kb = q / (NSB * LS), rem = q - kb * (NSB * LS);
+            int k = 2 * kb + half;
             int l = rem / LS, s = rem - l * LS;
             if (l < nloc) {
-              size_t o = (size_t)k * stride + site0 * LS + rem;
+              size_t o = (((size_t)kb * stride + site0 * LS + rem) << 1) + half;
               V pv = buf[(k * NSB + l) * PITCH + s];
               __stcs(gpsi + o, vfma(upd.a, pv, sv[c]));
               V pn = vfma(upd.b, pv, rv[c]);
@@ -118,9 +124,11 @@ __global__ void __launch_bounds__(NSB* VecOf<T>::NB, 2) k_s_sweep(size_t n4, con
 #pragma unroll
     for (int it = 0; it < LS; it++) {
       int idx = threadIdx.x + it * NT;
-      int k = idx / (NSB * LS), rem = idx - k * (NSB * LS);
+      int half = idx & 1, q = idx >> 1;
+      int kb = q / (NSB * LS), rem = q - kb * (NSB * LS);
+      int k = 2 * kb + half;
       int l = rem / LS, s = rem - l * LS;
-      if (l < nloc) __stcs(gout + (size_t)k * stride + site0 * LS + rem, buf[(k * NSB + l) * PITCH + s]);
+      if (l < nloc) __stcs(gout + (((size_t)kb * stride + site0 * LS + rem) << 1) + half, buf[(k * NSB + l) * PITCH + s]);
     }
     __syncthreads();  // buf is refilled by the prefetch of the next iteration
   }
