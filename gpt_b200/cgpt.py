@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _here = os.path.dirname(os.path.abspath(__file__))
-LIBRARY_PATH = os.path.join(_here, "lib", "libcgpt_b200.so")
+LIBRARY_PATH = os.environ.get("GPT_B200_LIBRARY", os.path.join(_here, "lib", "libcgpt_b200.so"))  # override: A/B builds
 
 SINGLE, DOUBLE = 0, 1
 EVEN, ODD, FULL = 0, 1, 2

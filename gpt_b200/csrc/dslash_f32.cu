@@ -41,6 +41,23 @@ __device__ __forceinline__ void load_spinor_c32(const float* __restrict__ base, 
   }
 }
 
+// same with the three plane base pointers precomputed (uniform) and a 32-bit site index: two integer
+// instructions per plane instead of a 64-bit multiply-add chain
+__device__ __forceinline__ void load_spinor_c32_planes(const float* __restrict__ p0, const float* __restrict__ p1,
+                                                       const float* __restrict__ p2, unsigned site, c32 (&p)[12]) {
+  const size_t off = (size_t)site * 8;
+  float v[8];
+  ld256(p0 + off, v);
+#pragma unroll
+  for (int e = 0; e < 4; e++) p[e] = pk(v[2 * e], v[2 * e + 1]);
+  ld256(p1 + off, v);
+#pragma unroll
+  for (int e = 0; e < 4; e++) p[4 + e] = pk(v[2 * e], v[2 * e + 1]);
+  ld256(p2 + off, v);
+#pragma unroll
+  for (int e = 0; e < 4; e++) p[8 + e] = pk(v[2 * e], v[2 * e + 1]);
+}
+
 template <bool STREAM>
 __device__ __forceinline__ void store_spinor_c32(float* __restrict__ base, size_t nsites, size_t site, const c32 (&p)[12]) {
 #pragma unroll
@@ -182,16 +199,17 @@ __device__ __forceinline__ void load_link_smem(const float4* __restrict__ slinks
 }
 
 // one direction for the SPER s-slices a thread owns: the link is read once, the spinors are independent loads
-template <int MU, bool FWD, bool DAG, int LS, int SPER, int ABL>
+template <int MU, bool FWD, bool DAG, int LS, int SPER, int ABL, bool COMM>
 __device__ __forceinline__ void hop_tile(c32 (&acc)[SPER][12], const Geom& g, int x, int y, int z, int t, int l, int j, int i4,
                                          const float* __restrict__ in, size_t in_stride, const float4* __restrict__ slinks) {
   constexpr int TPS = LS / SPER;
-  if (off_rank<MU, FWD>(g, x, y, z, t)) return;
+  if (COMM && off_rank<MU, FWD>(g, x, y, z, t)) return;  // COMM = false: single GPU, no boundary predicates at all
   int n4 = neighbor<MU, FWD>(g, x, y, z, t);
   if (ABL == 1) n4 = i4;
   c32 psi[SPER][12];
 #pragma unroll
-  for (int r = 0; r < SPER; r++) load_spinor_c32(in, in_stride, (size_t)n4 * LS + j + r * TPS, psi[r]);
+  for (int r = 0; r < SPER; r++)
+    load_spinor_c32_planes(in, in + in_stride * 8, in + in_stride * 16, (unsigned)(n4 * LS + j + r * TPS), psi[r]);
   if (ABL == 2) {
 #pragma unroll
     for (int r = 0; r < SPER; r++)
@@ -218,7 +236,7 @@ struct EpiArgs {
   SweepParams<float> P;
 };
 
-template <bool DAG, int LS, int SPER, int NS, int MINB, int ABL, bool EPI>
+template <bool DAG, int LS, int SPER, int NS, int MINB, int ABL, bool EPI, bool COMM>
 __global__ void __launch_bounds__(NS* LS / SPER, MINB)
     k_dhop_f32_tile(Geom g, TileGeom tg, int p_out, const float* __restrict__ in, size_t in_stride, float* __restrict__ out,
                     size_t out_stride, const float* __restrict__ links, EpiArgs epi) {
@@ -263,14 +281,14 @@ __global__ void __launch_bounds__(NS* LS / SPER, MINB)
     for (int k = 0; k < 12; k++) acc[r][k] = 0ull;
   asm volatile("cp.async.wait_group 0;");
   __syncthreads();
-  hop_tile<0, true, DAG, LS, SPER, ABL>(acc, g, x, y, z, t, l, j, i4, in, in_stride, slinks);
-  hop_tile<0, false, DAG, LS, SPER, ABL>(acc, g, x, y, z, t, l, j, i4, in, in_stride, slinks);
-  hop_tile<1, true, DAG, LS, SPER, ABL>(acc, g, x, y, z, t, l, j, i4, in, in_stride, slinks);
-  hop_tile<1, false, DAG, LS, SPER, ABL>(acc, g, x, y, z, t, l, j, i4, in, in_stride, slinks);
-  hop_tile<2, true, DAG, LS, SPER, ABL>(acc, g, x, y, z, t, l, j, i4, in, in_stride, slinks);
-  hop_tile<2, false, DAG, LS, SPER, ABL>(acc, g, x, y, z, t, l, j, i4, in, in_stride, slinks);
-  hop_tile<3, true, DAG, LS, SPER, ABL>(acc, g, x, y, z, t, l, j, i4, in, in_stride, slinks);
-  hop_tile<3, false, DAG, LS, SPER, ABL>(acc, g, x, y, z, t, l, j, i4, in, in_stride, slinks);
+  hop_tile<0, true, DAG, LS, SPER, ABL, COMM>(acc, g, x, y, z, t, l, j, i4, in, in_stride, slinks);
+  hop_tile<0, false, DAG, LS, SPER, ABL, COMM>(acc, g, x, y, z, t, l, j, i4, in, in_stride, slinks);
+  hop_tile<1, true, DAG, LS, SPER, ABL, COMM>(acc, g, x, y, z, t, l, j, i4, in, in_stride, slinks);
+  hop_tile<1, false, DAG, LS, SPER, ABL, COMM>(acc, g, x, y, z, t, l, j, i4, in, in_stride, slinks);
+  hop_tile<2, true, DAG, LS, SPER, ABL, COMM>(acc, g, x, y, z, t, l, j, i4, in, in_stride, slinks);
+  hop_tile<2, false, DAG, LS, SPER, ABL, COMM>(acc, g, x, y, z, t, l, j, i4, in, in_stride, slinks);
+  hop_tile<3, true, DAG, LS, SPER, ABL, COMM>(acc, g, x, y, z, t, l, j, i4, in, in_stride, slinks);
+  hop_tile<3, false, DAG, LS, SPER, ABL, COMM>(acc, g, x, y, z, t, l, j, i4, in, in_stride, slinks);
 
   if (EPI) {
     constexpr int PITCH = LS + 1;
@@ -410,12 +428,12 @@ static bool make_tiles(const Geom& g, int ns, TileGeom& tg) {
   return true;
 }
 
-template <bool DAG, int LS, int SPER, int NS, int MINB, int ABL, bool EPI>
+template <bool DAG, int LS, int SPER, int NS, int MINB, int ABL, bool EPI, bool COMM = false>
 static void launch_tile_k(const Geom& g, const TileGeom& tg, int p_out, const float* in, size_t is, float* out, size_t os,
                           const float* links, const EpiArgs& epi) {
   dim3 blocks(tg.nxh, tg.ny, tg.nz * tg.nt);
   size_t smem = (size_t)NS * LINK_F4 * 16 + (EPI ? (size_t)6 * NS * (LS + 1) * 16 : 0);
-  auto kern = k_dhop_f32_tile<DAG, LS, SPER, NS, MINB, ABL, EPI>;
+  auto kern = k_dhop_f32_tile<DAG, LS, SPER, NS, MINB, ABL, EPI, COMM>;
   static bool configured = false;
   if (!configured) {
     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -440,6 +458,8 @@ static bool launch_tile_t(const Geom& g, int p_out, const float* in, size_t is, 
     launch_tile_k<DAG, LS, SPER, NS, MINB, 1, false>(g, tg, p_out, in, is, out, os, links, none);
   else if (abl == 2)
     launch_tile_k<DAG, LS, SPER, NS, MINB, 2, false>(g, tg, p_out, in, is, out, os, links, none);
+  else if (g.comm_mask)
+    launch_tile_k<DAG, LS, SPER, NS, MINB, 0, false, true>(g, tg, p_out, in, is, out, os, links, none);
   else
     launch_tile_k<DAG, LS, SPER, NS, MINB, 0, false>(g, tg, p_out, in, is, out, os, links, none);
   return true;
