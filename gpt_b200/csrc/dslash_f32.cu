@@ -503,6 +503,10 @@ void dhop_half_f32(cgptb_fermion_operator* op, bool dag, const float* pin, size_
   static int no_tiles = env_int("CGPTB_NO_TILES", 0);
   const float* links = (const float*)op->links[p_out];
   bool done = false;
+  if (dhop_tma_usable(op)) {
+    dhop_half_f32_tma(op, dag, pin, in_stride, pout, out_stride, p_out);
+    return;
+  }
   if (!no_tiles) done = dag ? launch_tiled<true>(ls, op->g, p_out, pin, in_stride, pout, out_stride, links, 0)
                             : launch_tiled<false>(ls, op->g, p_out, pin, in_stride, pout, out_stride, links, 0);
   if (!done) {

@@ -1,0 +1,463 @@
+// Single-precision hopping term as a persistent, TMA-fed sweep along t ("3.5D blocking") for sm_100a.
+//
+// Why: the register/L1-based kernels in dslash_f32.cu re-fetch every neighbour spinor through L1/L2 (about 4.8 of the 8
+// neighbour reads miss L1), spend ~45 % of their instructions on neighbour index arithmetic and can keep only one or two
+// hops of loads in flight per thread.  Here the loads are issued by one producer warp with cp.async.bulk.tensor (TMA)
+// into a shared-memory ring, completely decoupled from the arithmetic:
+//
+//   * work item = (4x4x4 tile of checkerboard sites in (x/2, y, z)) x (chunk of SC = 4 fifth-dimension slices) x (range
+//     of TRL time slices); a persistent CTA (one per SM) walks its items and sweeps each along t;
+//   * per time slice the producer loads, for each of the three 32-byte component planes, the centre box of the tile
+//     (64 sites) and its six (x/2, y, z) faces (16 sites each) -- 21 box loads with the 128-byte swizzle, each shared
+//     memory row being the 4 x 32 B of one site -- plus the tile's 64 x 8 links (one box of the padded link array):
+//     2.5 spinor loads per output site instead of 8, all address arithmetic done by the TMA unit;
+//   * the +-t neighbours never travel twice: the thread that owns (site, s) reads its own entry of the centre box once
+//     per slice, uses it for the forward-t hop of the output one slice back (kept open in registers with its U_t) and
+//     carries it to the backward-t hop of the next slice;
+//   * 256 compute threads = 64 sites x 4 s; a neighbour spinor is six conflict-free LDS.128 at (slot base + per-thread
+//     constant + immediate), the site's links are broadcast LDS.128; arithmetic is the packed FFMA2 code of packed.cuh.
+//
+// Reference semantics: Grid's DhopEO/DhopOE behind cgpt opcodes 3002/4002 (lib/cgpt/lib/operators/register.h:2-20),
+// restated in lib/gpt/qcd/fermion/reference/wilson_clover.py:182-200.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <stdlib.h>
+#include <string.h>
+#include "dslash.cuh"
+#include "operator.cuh"
+#include "packed.cuh"
+
+namespace cgptb {
+
+namespace tma {
+constexpr int TX = 4, TY = 4, TZ = 4;  // tile in checkerboard coordinates (x/2, y, z)
+constexpr int SC = 4;                  // fifth-dimension slices per chunk (4 x 32 B = one 128-byte swizzle row)
+constexpr int NS = TX * TY * TZ;       // 64 sites per time slice
+constexpr int NCOMP = NS * SC;         // compute threads
+constexpr int NTHREADS = NCOMP + 32;   // + producer warp
+constexpr int ROW_B = 128;
+// one component plane of a slice slot: centre rows [z][y][x], then the six faces (16 rows each)
+constexpr int OFF_C = 0, OFF_XM = 8192, OFF_XP = 10240, OFF_YM = 12288, OFF_YP = 14336, OFF_ZM = 16384, OFF_ZP = 18432;
+constexpr int PLANE_B = 20480;
+constexpr int SLOT_B = 3 * PLANE_B;            // 61440
+constexpr int CENTER_B = 3 * NS * ROW_B;       // 24576: bytes of a centre-only load
+constexpr int LINK_ROW_F = 148;                // floats per site in the padded link array (8 x 18 + 4)
+constexpr int LINK_ROW_B = LINK_ROW_F * 4;     // 592: bank shift 20 words per site
+constexpr int LINK_B = NS * LINK_ROW_B;        // 37888
+constexpr int NSLOT = 2;
+constexpr int SMEM_B = NSLOT * (SLOT_B + LINK_B) + 64 + 1024;  // + barriers + alignment slack
+
+struct Geo {
+  int hx, Ly, Lz, T;
+  int nbx, nby, nbz, nchunk;
+  int trl, ntr, nitems;
+  int tp;  // component-plane stride of the input field in units of time slices
+  int p_out;
+  int ls;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// wait for the phase with the given parity; a wait that never completes (a lost transaction count) traps instead of
+// hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; spin++) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+// spinor of one (site, s) from a slice slot: a = byte address of the low 16-byte chunk of plane 0 (swizzle applied)
+__device__ __forceinline__ void lds_spinor(uint32_t a, c32 (&p)[12]) {
+  const uint32_t b = a ^ 16u;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(p[4 * k]), "=l"(p[4 * k + 1]) : "r"(a + k * PLANE_B));
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(p[4 * k + 2]), "=l"(p[4 * k + 3]) : "r"(b + k * PLANE_B));
+  }
+}
+
+// link D of a site (row = shared address of the site's 592-byte row): 72 B, 16-byte aligned for even D, 8 mod 16 for odd D
+template <int D>
+__device__ __forceinline__ void lds_link(uint32_t row, float (&wr)[9], float (&wi)[9]) {
+  const uint32_t a = row + D * 72;
+  float v[18];
+  if (D % 2 == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[4 * k]), "=f"(v[4 * k + 1]), "=f"(v[4 * k + 2]), "=f"(v[4 * k + 3]) : "r"(a + 16 * k));
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[16]), "=f"(v[17]) : "r"(a + 64));
+  } else {
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "r"(a));
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[2 + 4 * k]), "=f"(v[3 + 4 * k]), "=f"(v[4 + 4 * k]), "=f"(v[5 + 4 * k]) : "r"(a + 8 + 16 * k));
+  }
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    wr[k] = v[2 * k];
+    wi[k] = v[2 * k + 1];
+  }
+}
+
+// acc += recon( W(^dag) proj psi ), same arithmetic as hop_core of dslash_f32.cu
+template <int MU, bool FWD, bool DAG>
+__device__ __forceinline__ void hop_math(c32 (&acc)[12], const c32 (&psi)[12], const float (&wr)[9], const float (&wi)[9]) {
+  const int SGN = (FWD != DAG) ? -1 : +1;
+  typedef Proj<MU, SGN> P;
+  c32 h[6];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    h[c] = add2(psi[c], times_iph<P::A>(psi[P::J0 * 3 + c]));
+    h[3 + c] = add2(psi[3 + c], times_iph<P::B>(psi[P::J1 * 3 + c]));
+  }
+  c32 chi[6];
+#pragma unroll
+  for (int sp = 0; sp < 2; sp++) {
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      c32 a;
+      if (FWD) {
+        a = cmul<false>(wr[r * 3 + 0], wi[r * 3 + 0], h[sp * 3 + 0]);
+        a = cmac<false>(a, wr[r * 3 + 1], wi[r * 3 + 1], h[sp * 3 + 1]);
+        a = cmac<false>(a, wr[r * 3 + 2], wi[r * 3 + 2], h[sp * 3 + 2]);
+      } else {
+        a = cmul<true>(wr[0 * 3 + r], wi[0 * 3 + r], h[sp * 3 + 0]);
+        a = cmac<true>(a, wr[1 * 3 + r], wi[1 * 3 + r], h[sp * 3 + 1]);
+        a = cmac<true>(a, wr[2 * 3 + r], wi[2 * 3 + r], h[sp * 3 + 2]);
+      }
+      chi[sp * 3 + r] = a;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    acc[c] = add2(acc[c], chi[c]);
+    acc[3 + c] = add2(acc[3 + c], chi[3 + c]);
+    acc[6 + c] = add2(acc[6 + c], times_iph<P::C2>(chi[P::K2 * 3 + c]));
+    acc[9 + c] = add2(acc[9 + c], times_iph<P::C3>(chi[P::K3 * 3 + c]));
+  }
+}
+
+template <int MU, bool FWD, bool DAG, int D>
+__device__ __forceinline__ void hop_smem(c32 (&acc)[12], uint32_t spinor_addr, uint32_t link_row) {
+  c32 psi[12];
+  float wr[9], wi[9];
+  lds_spinor(spinor_addr, psi);
+  lds_link<D>(link_row, wr, wi);
+  hop_math<MU, FWD, DAG>(acc, psi, wr, wi);
+}
+
+struct Item {
+  int c, xh0, y0, z0, t0;
+};
+__device__ __forceinline__ Item decode_item(const Geo& G, int item) {
+  Item it;
+  it.c = item % G.nchunk;
+  int r = item / G.nchunk;
+  it.xh0 = (r % G.nbx) * TX;
+  r /= G.nbx;
+  it.y0 = (r % G.nby) * TY;
+  r /= G.nby;
+  it.z0 = (r % G.nbz) * TZ;
+  it.t0 = (r / G.nbz) * G.trl;
+  return it;
+}
+
+template <bool DAG>
+__global__ void __launch_bounds__(NTHREADS, 1)
+    k_dhop_f32_tma(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmX,
+                   const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmZ,
+                   const __grid_constant__ CUtensorMap tmL, const Geo G, float* __restrict__ out, size_t out_stride) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t s_spin = sbase;
+  const uint32_t s_link = sbase + NSLOT * SLOT_B;
+  const uint32_t s_bar = s_link + NSLOT * LINK_B;  // full[0], full[1], empty[0], empty[1]
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < NSLOT; i++) {
+      mbar_init(s_bar + 8 * i, 1);
+      mbar_init(s_bar + 8 * (NSLOT + i), NCOMP / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == NCOMP / 32) {
+    // ---------------- producer: one elected lane issues the box loads of a slice ----------------------------
+    uint32_t g = 0;
+    for (int item = blockIdx.x; item < G.nitems; item += gridDim.x) {
+      const Item it = decode_item(G, item);
+      const int s0f = it.c * SC * 8;
+      const int xm = (it.xh0 == 0 ? G.hx : it.xh0) - 1, xp = it.xh0 + TX == G.hx ? 0 : it.xh0 + TX;
+      const int ym = (it.y0 == 0 ? G.Ly : it.y0) - 1, yp = it.y0 + TY == G.Ly ? 0 : it.y0 + TY;
+      const int zm = (it.z0 == 0 ? G.Lz : it.z0) - 1, zp = it.z0 + TZ == G.Lz ? 0 : it.z0 + TZ;
+      for (int st = 0; st <= G.trl + 1; st++, g++) {
+        int tau = it.t0 - 1 + st;
+        if (tau < 0) tau += G.T;
+        if (tau >= G.T) tau -= G.T;
+        const bool full_step = st >= 1 && st <= G.trl;
+        const uint32_t slot = g & 1u, ph = (g >> 1) & 1u;
+        const uint32_t bar = s_bar + 8 * slot;
+        if (lane == 0) {
+          mbar_wait(s_bar + 8 * (NSLOT + slot), ph ^ 1u);
+          const uint32_t dst = s_spin + slot * SLOT_B;
+          if (full_step) {
+            mbar_expect_tx(bar, (uint32_t)(SLOT_B + LINK_B));
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+              const int tq = k * G.tp + tau;
+              const uint32_t d = dst + k * PLANE_B;
+              tma_load_5d(d + OFF_C, &tmC, bar, s0f, it.xh0, it.y0, it.z0, tq);
+              tma_load_5d(d + OFF_XM, &tmX, bar, s0f, xm, it.y0, it.z0, tq);
+              tma_load_5d(d + OFF_XP, &tmX, bar, s0f, xp, it.y0, it.z0, tq);
+              tma_load_5d(d + OFF_YM, &tmY, bar, s0f, it.xh0, ym, it.z0, tq);
+              tma_load_5d(d + OFF_YP, &tmY, bar, s0f, it.xh0, yp, it.z0, tq);
+              tma_load_5d(d + OFF_ZM, &tmZ, bar, s0f, it.xh0, it.y0, zm, tq);
+              tma_load_5d(d + OFF_ZP, &tmZ, bar, s0f, it.xh0, it.y0, zp, tq);
+            }
+            tma_load_5d(s_link + slot * LINK_B, &tmL, bar, 0, it.xh0, it.y0, it.z0, tau);
+          } else {
+            mbar_expect_tx(bar, (uint32_t)CENTER_B);
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+              tma_load_5d(dst + k * PLANE_B + OFF_C, &tmC, bar, s0f, it.xh0, it.y0, it.z0, k * G.tp + tau);
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumers: thread = (site l of the tile, slice j of the chunk) -------------------------
+  const int l = tid >> 2, j = tid & 3;
+  const int lx = l & 3, ly = (l >> 2) & 3, lz = l >> 4;
+  auto rowaddr = [&](int buf, int row) -> uint32_t { return (uint32_t)(buf + row * ROW_B + (((2 * j) ^ (row & 7)) << 4)); };
+  const uint32_t a_own = rowaddr(OFF_C, l);
+  const uint32_t a_left = lx > 0 ? rowaddr(OFF_C, l - 1) : rowaddr(OFF_XM, lz * TY + ly);
+  const uint32_t a_right = lx < TX - 1 ? rowaddr(OFF_C, l + 1) : rowaddr(OFF_XP, lz * TY + ly);
+  const uint32_t a_yp = ly < TY - 1 ? rowaddr(OFF_C, l + TX) : rowaddr(OFF_YP, lz * TX + lx);
+  const uint32_t a_ym = ly > 0 ? rowaddr(OFF_C, l - TX) : rowaddr(OFF_YM, lz * TX + lx);
+  const uint32_t a_zp = lz < TZ - 1 ? rowaddr(OFF_C, l + TX * TY) : rowaddr(OFF_ZP, ly * TX + lx);
+  const uint32_t a_zm = lz > 0 ? rowaddr(OFF_C, l - TX * TY) : rowaddr(OFF_ZM, ly * TX + lx);
+  const int b0 = (ly + lz + G.p_out) & 1;  // tile origins are even
+  const int slice_sites = G.hx * G.Ly * G.Lz;
+
+  c32 acc[12], carry[12];
+  float utr[9], uti[9];
+#pragma unroll
+  for (int k = 0; k < 12; k++) acc[k] = carry[k] = 0ull;
+#pragma unroll
+  for (int k = 0; k < 9; k++) utr[k] = uti[k] = 0.f;
+
+  uint32_t g = 0;
+  for (int item = blockIdx.x; item < G.nitems; item += gridDim.x) {
+    const Item it = decode_item(G, item);
+    const int site0 = (it.xh0 + lx) + G.hx * ((it.y0 + ly) + G.Ly * (it.z0 + lz));
+    const int s = it.c * SC + j;
+    int tau_prev = 0;
+    for (int st = 0; st <= G.trl + 1; st++, g++) {
+      int tau = it.t0 - 1 + st;
+      if (tau < 0) tau += G.T;
+      if (tau >= G.T) tau -= G.T;
+      const uint32_t slot = g & 1u, ph = (g >> 1) & 1u;
+      mbar_wait(s_bar + 8 * slot, ph);
+      const uint32_t sp = s_spin + slot * SLOT_B;
+      const uint32_t lrow = s_link + slot * LINK_B + l * LINK_ROW_B;
+      c32 own[12];
+      lds_spinor(sp + a_own, own);
+      if (st >= 2) {
+        // forward-t hop closes the output of the previous slice
+        hop_math<3, true, DAG>(acc, own, utr, uti);
+        const size_t site = ((size_t)site0 + (size_t)slice_sites * tau_prev) * G.ls + s;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 4; e++) upk(acc[4 * k + e], v[2 * e], v[2 * e + 1]);
+          st256_cs(out + (k * out_stride + site) * 8, v);
+        }
+      }
+      if (st >= 1 && st <= G.trl) {
+#pragma unroll
+        for (int k = 0; k < 12; k++) acc[k] = 0ull;
+        {
+          float wr[9], wi[9];
+          lds_link<7>(lrow, wr, wi);
+          hop_math<3, false, DAG>(acc, carry, wr, wi);
+        }
+        const int b = (b0 + tau) & 1;
+        const uint32_t a_xp = b ? a_right : a_own, a_xm = b ? a_own : a_left;
+        hop_smem<0, true, DAG, 0>(acc, sp + a_xp, lrow);
+        hop_smem<0, false, DAG, 4>(acc, sp + a_xm, lrow);
+        hop_smem<1, true, DAG, 1>(acc, sp + a_yp, lrow);
+        hop_smem<1, false, DAG, 5>(acc, sp + a_ym, lrow);
+        hop_smem<2, true, DAG, 2>(acc, sp + a_zp, lrow);
+        hop_smem<2, false, DAG, 6>(acc, sp + a_zm, lrow);
+        lds_link<3>(lrow, utr, uti);
+      }
+#pragma unroll
+      for (int k = 0; k < 12; k++) carry[k] = own[k];
+      tau_prev = tau;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_bar + 8 * (NSLOT + slot));
+    }
+  }
+}
+
+__global__ void k_pad_links(size_t n4, const float* __restrict__ links, float* __restrict__ padded) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4 * (LINK_ROW_F / 4)) return;
+  size_t site = i / (LINK_ROW_F / 4);
+  int q = (int)(i - site * (LINK_ROW_F / 4));
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (q < 36) v = reinterpret_cast<const float4*>(links)[site * 36 + q];
+  reinterpret_cast<float4*>(padded)[i] = v;
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 encoder() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = 0;
+  if (!fn) {
+    void* p = 0;
+    cudaDriverEntryPointQueryResult q;
+    CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || !p) CGPTB_ERR("cuTensorMapEncodeTiled is not available from this driver");
+    fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+  }
+  return fn;
+}
+
+static void encode5(CUtensorMap* m, const void* base, const cuuint64_t (&dims)[5], const cuuint64_t (&strides)[4],
+                    const cuuint32_t (&box)[5], CUtensorMapSwizzle sw) {
+  const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = encoder()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(base), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) CGPTB_ERR("cuTensorMapEncodeTiled failed with code %d", (int)r);
+}
+
+static int env_i(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+}  // namespace tma
+
+// true if the TMA sweep kernel handles this operator / lattice (single GPU, Ls a multiple of 4, extents divisible by
+// the tile); the caller falls back to the kernels of dslash_f32.cu otherwise
+bool dhop_tma_usable(const cgptb_fermion_operator* op) {
+  if (tma::env_i("CGPTB_NO_TMA", 0) || op->prec != CGPTB_SINGLE || op->g.comm_mask) return false;
+  const Geom& g = op->g;
+  if (op->ls() % tma::SC) return false;
+  if (g.hx % tma::TX || g.L[1] % tma::TY || g.L[2] % tma::TZ || g.L[3] < 2) return false;
+  return true;
+}
+
+void dhop_tma_release(cgptb_fermion_operator* op) {
+  for (int p = 0; p < 2; p++)
+    if (op->links_pad[p]) {
+      cudaFree(op->links_pad[p]);
+      op->links_pad[p] = 0;
+    }
+}
+
+void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, size_t in_stride, float* pout, size_t out_stride,
+                       int p_out) {
+  using namespace tma;
+  const Geom& g = op->g;
+  const int ls = op->ls();
+  if (!op->links_pad_valid) {
+    size_t n4 = (size_t)g.half4;
+    for (int p = 0; p < 2; p++) {
+      if (!op->links_pad[p]) CUDA_CHECK(cudaMalloc(&op->links_pad[p], n4 * LINK_ROW_B));
+      size_t n = n4 * (LINK_ROW_F / 4);
+      k_pad_links<<<(unsigned)((n + 255) / 256), 256, 0, g_stream>>>(n4, (const float*)op->links[p], (float*)op->links_pad[p]);
+      LAUNCH_CHECK();
+    }
+    op->links_pad_valid = true;
+  }
+  Geo G;
+  G.hx = g.hx;
+  G.Ly = g.L[1];
+  G.Lz = g.L[2];
+  G.T = g.L[3];
+  G.nbx = g.hx / TX;
+  G.nby = g.L[1] / TY;
+  G.nbz = g.L[2] / TZ;
+  G.nchunk = ls / SC;
+  const int trl_max = env_i("CGPTB_TMA_TRL", 16);  // time slices per work item: the largest divisor of T below the cap
+  int trl = 1;
+  for (int d = 1; d <= G.T && d <= trl_max; d++)
+    if (G.T % d == 0) trl = d;
+  G.trl = trl;
+  G.ntr = G.T / trl;
+  G.nitems = G.nchunk * G.nbx * G.nby * G.nbz * G.ntr;
+  const size_t slice_blocks = (size_t)g.hx * g.L[1] * g.L[2] * ls;  // 32-byte blocks per time slice
+  CGPTB_ASSERT(in_stride % slice_blocks == 0);
+  G.tp = (int)(in_stride / slice_blocks);
+  G.p_out = p_out;
+  G.ls = ls;
+
+  CUtensorMap tmC, tmX, tmY, tmZ, tmL;
+  {
+    const cuuint64_t dims[5] = {(cuuint64_t)ls * 8, (cuuint64_t)g.hx, (cuuint64_t)g.L[1], (cuuint64_t)g.L[2],
+                                (cuuint64_t)2 * G.tp + g.L[3]};
+    const cuuint64_t row = (cuuint64_t)ls * 32;
+    const cuuint64_t strides[4] = {row, row * g.hx, row * g.hx * g.L[1], row * g.hx * g.L[1] * g.L[2]};
+    const cuuint32_t bc[5] = {SC * 8, TX, TY, TZ, 1}, bx[5] = {SC * 8, 1, TY, TZ, 1}, by[5] = {SC * 8, TX, 1, TZ, 1},
+                     bz[5] = {SC * 8, TX, TY, 1, 1};
+    encode5(&tmC, pin, dims, strides, bc, CU_TENSOR_MAP_SWIZZLE_128B);
+    encode5(&tmX, pin, dims, strides, bx, CU_TENSOR_MAP_SWIZZLE_128B);
+    encode5(&tmY, pin, dims, strides, by, CU_TENSOR_MAP_SWIZZLE_128B);
+    encode5(&tmZ, pin, dims, strides, bz, CU_TENSOR_MAP_SWIZZLE_128B);
+  }
+  {
+    const cuuint64_t dims[5] = {(cuuint64_t)LINK_ROW_F, (cuuint64_t)g.hx, (cuuint64_t)g.L[1], (cuuint64_t)g.L[2], (cuuint64_t)g.L[3]};
+    const cuuint64_t row = LINK_ROW_B;
+    const cuuint64_t strides[4] = {row, row * g.hx, row * g.hx * g.L[1], row * g.hx * g.L[1] * g.L[2]};
+    const cuuint32_t bl[5] = {LINK_ROW_F, TX, TY, TZ, 1};
+    encode5(&tmL, op->links_pad[p_out], dims, strides, bl, CU_TENSOR_MAP_SWIZZLE_NONE);
+  }
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(k_dhop_f32_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B));
+    CUDA_CHECK(cudaFuncSetAttribute(k_dhop_f32_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B));
+    configured = true;
+  }
+  const int grid_env = env_i("CGPTB_TMA_GRID", 0);
+  int grid = grid_env > 0 ? grid_env : sm_count();
+  if (grid > G.nitems) grid = G.nitems;
+  if (dag)
+    k_dhop_f32_tma<true><<<grid, NTHREADS, SMEM_B, g_stream>>>(tmC, tmX, tmY, tmZ, tmL, G, pout, out_stride);
+  else
+    k_dhop_f32_tma<false><<<grid, NTHREADS, SMEM_B, g_stream>>>(tmC, tmX, tmY, tmZ, tmL, G, pout, out_stride);
+  LAUNCH_CHECK();
+}
+
+}  // namespace cgptb

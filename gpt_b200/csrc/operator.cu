@@ -666,6 +666,7 @@ static void import_gauge_t(cgptb_fermion_operator* op, const cgptb_lattice* cons
     lc.gL[mu] = op->gL[mu];
   }
   size_t link_bytes = (size_t)op->g.half4 * 8 * 18 * sizeof(T);
+  op->links_pad_valid = false;
   int threads = 128;
   unsigned blocks = (unsigned)((op->g.half4 + threads - 1) / threads);
   for (int p = 0; p < 2; p++) {
@@ -995,6 +996,7 @@ int cgptb_set_mass_fermion_operator(cgptb_fermion_operator* op, const cgptb_ferm
 int cgptb_delete_fermion_operator(cgptb_fermion_operator* op) {
   CGPTB_API_BEGIN
   if (op) {
+    dhop_tma_release(op);
     for (int p = 0; p < 2; p++) {
       if (op->links[p]) cudaFree(op->links[p]);
       if (op->clov[p]) cudaFree(op->clov[p]);

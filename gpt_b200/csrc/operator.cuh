@@ -20,6 +20,8 @@ struct cgptb_fermion_operator {
   cgptb::Geom g;
   cgptb_fermion_params p;
   void* links[2] = {0, 0};      // per output parity: [half4][8][9] complex, -c_mu/2 and phases folded in
+  void* links_pad[2] = {0, 0};  // the same links in 592-byte rows for the TMA sweep kernel (dslash_tma.cu), built lazily
+  bool links_pad_valid = false;
   bool has_clover = false;
   void* clov[2] = {0, 0};       // per parity: [72][half4] reals
   void* clov_inv[2] = {0, 0};
@@ -51,6 +53,11 @@ void op_apply(cgptb_fermion_operator* op, int opcode, const cgptb_lattice* src, 
 // sweep.cu: fused fifth-dimension operators; T = (b + c S5)(bee - cee S5)^-1 = Meooe5D o MooeeInv
 enum { SWEEP_T = 0, SWEEP_TDAG = 1, SWEEP_MINV = 2, SWEEP_MINVDAG = 3 };
 bool op_s_sweep(cgptb_fermion_operator* op, int mode, const cgptb_lattice* in, cgptb_lattice* out);
+// dslash_tma.cu
+bool dhop_tma_usable(const cgptb_fermion_operator* op);
+void dhop_tma_release(cgptb_fermion_operator* op);
+void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, size_t in_stride, float* pout, size_t out_stride,
+                       int p_out);
 // halo.cu
 void halo_setup(cgptb_fermion_operator* op, const cgptb_lattice* const U[4]);
 void halo_begin(cgptb_fermion_operator* op, bool dag, int p_out, const void* in, size_t in_stride);

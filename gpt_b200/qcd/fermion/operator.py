@@ -21,7 +21,8 @@ class interface:
     def _setup(self, name, grid, params):
         assert self.obj is None
         tag_params = {x: params[x] for x in params if x not in ["U", "mass", "mass_plus", "mass_minus"]}
-        tag = f"{name}_{grid.precision.cgpt_dtype}_{tag_params}"
+        # the reference's params carry the grid handles (U_grid, F_grid, ...), which makes the tag grid specific
+        tag = f"{name}_{grid.precision.cgpt_dtype}_{list(grid.fdimensions)}_{getattr(grid, 'mpi', None)}_{tag_params}"
         if tag in operator_limbo and len(operator_limbo[tag]) > 0:
             self.obj = operator_limbo[tag].pop()
             # set mass needs to precede update for clover-type fermions (interface.py:43-45)
