@@ -9,8 +9,10 @@
 //     of TRL time slices); a persistent CTA (one per SM) walks its items and sweeps each along t;
 //   * per time slice the producer loads, for each of the three 32-byte component planes, the centre box of the tile
 //     (64 sites) and its six (x/2, y, z) faces (16 sites each) -- 21 box loads with the 128-byte swizzle, each shared
-//     memory row being the 4 x 32 B of one site -- plus the tile's 64 x 8 links (one box of the padded link array):
+//     memory row being the 4 x 32 B of one site -- plus the tile's 64 x 8 links (two boxes of four links each):
 //     2.5 spinor loads per output site instead of 8, all address arithmetic done by the TMA unit;
+//   * only two stages (2 x 98 KB) fit into shared memory, so each stage is handed back in two halves (after the fourth
+//     and after the last hop of a step) and refilled in two halves: every byte is requested 1.5 steps ahead of its use;
 //   * the +-t neighbours never travel twice: the thread that owns (site, s) reads its own entry of the centre box once
 //     per slice, uses it for the forward-t hop of the output one slice back (kept open in registers with its U_t) and
 //     carries it to the backward-t hop of the next slice;
@@ -41,11 +43,18 @@ constexpr int OFF_C = 0, OFF_XM = 8192, OFF_XP = 10240, OFF_YM = 12288, OFF_YP =
 constexpr int PLANE_B = 20480;
 constexpr int SLOT_B = 3 * PLANE_B;            // 61440
 constexpr int CENTER_B = 3 * NS * ROW_B;       // 24576: bytes of a centre-only load
-constexpr int LINK_ROW_F = 148;                // floats per site in the padded link array (8 x 18 + 4)
-constexpr int LINK_ROW_B = LINK_ROW_F * 4;     // 592: bank shift 20 words per site
-constexpr int LINK_B = NS * LINK_ROW_B;        // 37888
+constexpr int FACE_B = 3 * 3 * (NS / TX) * ROW_B;  // 18432: three faces x three planes (the face part of one half step)
+// links come in two halves of four, in the order a step uses them: A = {t-, x+, x-, y+}, B = {y-, z+, z-, t+};
+// a row is 4 x 72 B + 16 B padding (bank shift of 12 words per site: the 8 sites a warp reads are conflict free)
+constexpr int LINK_ROW_F = 76;
+constexpr int LINK_ROW_B = LINK_ROW_F * 4;    // 304
+constexpr int LINK_HALF_B = NS * LINK_ROW_B;  // 19456
+constexpr int HALF_B = FACE_B + LINK_HALF_B;  // 37888: bytes signalled on full_A / full_B of a full step
 constexpr int NSLOT = 2;
-constexpr int SMEM_B = NSLOT * (SLOT_B + LINK_B) + 64 + 1024;  // + barriers + alignment slack
+constexpr int STAGE_B = SLOT_B + 2 * LINK_HALF_B;  // 100352
+// barriers per slot: full_C (centre), full_A, full_B, empty_A, empty_B
+constexpr int BAR_FC = 0, BAR_FA = 1, BAR_FB = 2, BAR_EA = 3, BAR_EB = 4, NBAR = 5;
+constexpr int SMEM_B = NSLOT * STAGE_B + NSLOT * NBAR * 8 + 1024;  // + alignment slack
 
 struct Geo {
   int hx, Ly, Lz, T;
@@ -102,12 +111,13 @@ __device__ __forceinline__ void lds_spinor(uint32_t a, c32 (&p)[12]) {
   }
 }
 
-// link D of a site (row = shared address of the site's 592-byte row): 72 B, 16-byte aligned for even D, 8 mod 16 for odd D
-template <int D>
+// link at position P (0..3) of a half row (row = shared address of the site's 304-byte row): 72 B each, 16-byte aligned
+// for even P, 8 mod 16 for odd P
+template <int P>
 __device__ __forceinline__ void lds_link(uint32_t row, float (&wr)[9], float (&wi)[9]) {
-  const uint32_t a = row + D * 72;
+  const uint32_t a = row + P * 72;
   float v[18];
-  if (D % 2 == 0) {
+  if (P % 2 == 0) {
 #pragma unroll
     for (int k = 0; k < 4; k++)
       asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[4 * k]), "=f"(v[4 * k + 1]), "=f"(v[4 * k + 2]), "=f"(v[4 * k + 3]) : "r"(a + 16 * k));
@@ -188,30 +198,39 @@ __device__ __forceinline__ Item decode_item(const Geo& G, int item) {
   return it;
 }
 
-template <bool DAG>
+// ABL (ablation, CGPTB_ABLATE): 0 production; 1 compute only (no TMA loads, the ring is signalled empty-handed);
+// 2 memory only (all loads and stores, no hop arithmetic)
+template <bool DAG, int ABL>
 __global__ void __launch_bounds__(NTHREADS, 1)
     k_dhop_f32_tma(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmX,
                    const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmZ,
                    const __grid_constant__ CUtensorMap tmL, const Geo G, float* __restrict__ out, size_t out_stride) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t s_spin = sbase;
-  const uint32_t s_link = sbase + NSLOT * SLOT_B;
-  const uint32_t s_bar = s_link + NSLOT * LINK_B;  // full[0], full[1], empty[0], empty[1]
+  const uint32_t s_bar = sbase + NSLOT * STAGE_B;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     for (int i = 0; i < NSLOT; i++) {
-      mbar_init(s_bar + 8 * i, 1);
-      mbar_init(s_bar + 8 * (NSLOT + i), NCOMP / 32);
+      const uint32_t b = s_bar + 8 * NBAR * i;
+      mbar_init(b + 8 * BAR_FC, 1);
+      mbar_init(b + 8 * BAR_FA, 1);
+      mbar_init(b + 8 * BAR_FB, 1);
+      mbar_init(b + 8 * BAR_EA, NCOMP / 32);
+      mbar_init(b + 8 * BAR_EB, NCOMP / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
   if (warp == NCOMP / 32) {
-    // ---------------- producer: one elected lane issues the box loads of a slice ----------------------------
+    // ---------------- producer: one elected lane -------------------------------------------------------------
+    // Each slot is refilled in two halves: A = faces x-, x+, y+ and links {t-, x+, x-, y+} as soon as the consumers are
+    // past the fourth hop of the step that used the slot, then the centre box and B = faces y-, z-, z+ and links
+    // {y-, z+, z-, t+} when the step is over.  Every byte is therefore requested 1.5 steps before it is needed although
+    // only two slots fit into shared memory.
+    if (lane != 0) return;
     uint32_t g = 0;
     for (int item = blockIdx.x; item < G.nitems; item += gridDim.x) {
       const Item it = decode_item(G, item);
@@ -225,30 +244,48 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         if (tau >= G.T) tau -= G.T;
         const bool full_step = st >= 1 && st <= G.trl;
         const uint32_t slot = g & 1u, ph = (g >> 1) & 1u;
-        const uint32_t bar = s_bar + 8 * slot;
-        if (lane == 0) {
-          mbar_wait(s_bar + 8 * (NSLOT + slot), ph ^ 1u);
-          const uint32_t dst = s_spin + slot * SLOT_B;
+        const uint32_t bar = s_bar + 8 * NBAR * slot;
+        const uint32_t dst = sbase + slot * STAGE_B;
+        const uint32_t dlink = dst + SLOT_B;
+        // half A
+        mbar_wait(bar + 8 * BAR_EA, ph ^ 1u);
+        if (ABL == 1 || !full_step) {
+          mbar_arrive(bar + 8 * BAR_FA);
+        } else {
+          mbar_expect_tx(bar + 8 * BAR_FA, (uint32_t)HALF_B);
+          tma_load_5d(dlink, &tmL, bar + 8 * BAR_FA, 0, it.xh0, it.y0, it.z0, tau);
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            const int tq = k * G.tp + tau;
+            const uint32_t d = dst + k * PLANE_B;
+            tma_load_5d(d + OFF_XP, &tmX, bar + 8 * BAR_FA, s0f, xp, it.y0, it.z0, tq);
+            tma_load_5d(d + OFF_XM, &tmX, bar + 8 * BAR_FA, s0f, xm, it.y0, it.z0, tq);
+            tma_load_5d(d + OFF_YP, &tmY, bar + 8 * BAR_FA, s0f, it.xh0, yp, it.z0, tq);
+          }
+        }
+        // centre and half B
+        mbar_wait(bar + 8 * BAR_EB, ph ^ 1u);
+        if (ABL == 1) {
+          mbar_arrive(bar + 8 * BAR_FC);
+          mbar_arrive(bar + 8 * BAR_FB);
+        } else {
+          mbar_expect_tx(bar + 8 * BAR_FC, (uint32_t)CENTER_B);
+#pragma unroll
+          for (int k = 0; k < 3; k++)
+            tma_load_5d(dst + k * PLANE_B + OFF_C, &tmC, bar + 8 * BAR_FC, s0f, it.xh0, it.y0, it.z0, k * G.tp + tau);
           if (full_step) {
-            mbar_expect_tx(bar, (uint32_t)(SLOT_B + LINK_B));
+            mbar_expect_tx(bar + 8 * BAR_FB, (uint32_t)HALF_B);
+            tma_load_5d(dlink + LINK_HALF_B, &tmL, bar + 8 * BAR_FB, 0, it.xh0, it.y0, it.z0, G.T + tau);
 #pragma unroll
             for (int k = 0; k < 3; k++) {
               const int tq = k * G.tp + tau;
               const uint32_t d = dst + k * PLANE_B;
-              tma_load_5d(d + OFF_C, &tmC, bar, s0f, it.xh0, it.y0, it.z0, tq);
-              tma_load_5d(d + OFF_XM, &tmX, bar, s0f, xm, it.y0, it.z0, tq);
-              tma_load_5d(d + OFF_XP, &tmX, bar, s0f, xp, it.y0, it.z0, tq);
-              tma_load_5d(d + OFF_YM, &tmY, bar, s0f, it.xh0, ym, it.z0, tq);
-              tma_load_5d(d + OFF_YP, &tmY, bar, s0f, it.xh0, yp, it.z0, tq);
-              tma_load_5d(d + OFF_ZM, &tmZ, bar, s0f, it.xh0, it.y0, zm, tq);
-              tma_load_5d(d + OFF_ZP, &tmZ, bar, s0f, it.xh0, it.y0, zp, tq);
+              tma_load_5d(d + OFF_YM, &tmY, bar + 8 * BAR_FB, s0f, it.xh0, ym, it.z0, tq);
+              tma_load_5d(d + OFF_ZP, &tmZ, bar + 8 * BAR_FB, s0f, it.xh0, it.y0, zp, tq);
+              tma_load_5d(d + OFF_ZM, &tmZ, bar + 8 * BAR_FB, s0f, it.xh0, it.y0, zm, tq);
             }
-            tma_load_5d(s_link + slot * LINK_B, &tmL, bar, 0, it.xh0, it.y0, it.z0, tau);
           } else {
-            mbar_expect_tx(bar, (uint32_t)CENTER_B);
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-              tma_load_5d(dst + k * PLANE_B + OFF_C, &tmC, bar, s0f, it.xh0, it.y0, it.z0, k * G.tp + tau);
+            mbar_arrive(bar + 8 * BAR_FB);
           }
         }
       }
@@ -287,15 +324,17 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       int tau = it.t0 - 1 + st;
       if (tau < 0) tau += G.T;
       if (tau >= G.T) tau -= G.T;
+      const bool full_step = st >= 1 && st <= G.trl;
       const uint32_t slot = g & 1u, ph = (g >> 1) & 1u;
-      mbar_wait(s_bar + 8 * slot, ph);
-      const uint32_t sp = s_spin + slot * SLOT_B;
-      const uint32_t lrow = s_link + slot * LINK_B + l * LINK_ROW_B;
+      const uint32_t bar = s_bar + 8 * NBAR * slot;
+      const uint32_t sp = sbase + slot * STAGE_B;
+      const uint32_t lrowA = sp + SLOT_B + l * LINK_ROW_B, lrowB = lrowA + LINK_HALF_B;
+      mbar_wait(bar + 8 * BAR_FC, ph);
       c32 own[12];
       lds_spinor(sp + a_own, own);
       if (st >= 2) {
         // forward-t hop closes the output of the previous slice
-        hop_math<3, true, DAG>(acc, own, utr, uti);
+        if (ABL != 2) hop_math<3, true, DAG>(acc, own, utr, uti);
         const size_t site = ((size_t)site0 + (size_t)slice_sites * tau_prev) * G.ls + s;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
@@ -305,41 +344,60 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           st256_cs(out + (k * out_stride + site) * 8, v);
         }
       }
-      if (st >= 1 && st <= G.trl) {
+      const int b = (b0 + tau) & 1;
+      const uint32_t a_xp = b ? a_right : a_own, a_xm = b ? a_own : a_left;
+      // ---- first half: t-, x+, x-, y+
+      mbar_wait(bar + 8 * BAR_FA, ph);
+      if (ABL == 2) {
+#pragma unroll
+        for (int k = 0; k < 12; k++) acc[k] = own[k];
+      } else if (full_step) {
 #pragma unroll
         for (int k = 0; k < 12; k++) acc[k] = 0ull;
         {
           float wr[9], wi[9];
-          lds_link<7>(lrow, wr, wi);
+          lds_link<0>(lrowA, wr, wi);
           hop_math<3, false, DAG>(acc, carry, wr, wi);
         }
-        const int b = (b0 + tau) & 1;
-        const uint32_t a_xp = b ? a_right : a_own, a_xm = b ? a_own : a_left;
-        hop_smem<0, true, DAG, 0>(acc, sp + a_xp, lrow);
-        hop_smem<0, false, DAG, 4>(acc, sp + a_xm, lrow);
-        hop_smem<1, true, DAG, 1>(acc, sp + a_yp, lrow);
-        hop_smem<1, false, DAG, 5>(acc, sp + a_ym, lrow);
-        hop_smem<2, true, DAG, 2>(acc, sp + a_zp, lrow);
-        hop_smem<2, false, DAG, 6>(acc, sp + a_zm, lrow);
-        lds_link<3>(lrow, utr, uti);
+        hop_smem<0, true, DAG, 1>(acc, sp + a_xp, lrowA);
+        hop_smem<0, false, DAG, 2>(acc, sp + a_xm, lrowA);
+        hop_smem<1, true, DAG, 3>(acc, sp + a_yp, lrowA);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar + 8 * BAR_EA);
+      // ---- second half: y-, z+, z-, and U_t for the forward-t hop of the next step
+      mbar_wait(bar + 8 * BAR_FB, ph);
+      if (ABL != 2 && full_step) {
+        hop_smem<1, false, DAG, 0>(acc, sp + a_ym, lrowB);
+        hop_smem<2, true, DAG, 1>(acc, sp + a_zp, lrowB);
+        hop_smem<2, false, DAG, 2>(acc, sp + a_zm, lrowB);
+        lds_link<3>(lrowB, utr, uti);
       }
 #pragma unroll
       for (int k = 0; k < 12; k++) carry[k] = own[k];
       tau_prev = tau;
       __syncwarp();
-      if (lane == 0) mbar_arrive(s_bar + 8 * (NSLOT + slot));
+      if (lane == 0) mbar_arrive(bar + 8 * BAR_EB);
     }
   }
 }
 
-__global__ void k_pad_links(size_t n4, const float* __restrict__ links, float* __restrict__ padded) {
+// links [site][8][9] complex -> [half][site][38] complex: half A = {t-, x+, x-, y+} = entries {7, 0, 4, 1}, half B = {y-, z+, z-,
+// t+} = entries {5, 2, 6, 3}, two complex of padding per row
+__global__ void k_pad_links(size_t n4, const float2* __restrict__ links, float2* __restrict__ padded) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n4 * (LINK_ROW_F / 4)) return;
-  size_t site = i / (LINK_ROW_F / 4);
-  int q = (int)(i - site * (LINK_ROW_F / 4));
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (q < 36) v = reinterpret_cast<const float4*>(links)[site * 36 + q];
-  reinterpret_cast<float4*>(padded)[i] = v;
+  if (i >= n4 * 2 * 38) return;
+  const int k = (int)(i % 38);
+  const size_t r = i / 38;
+  const size_t site = r % n4;
+  const int half = (int)(r / n4);
+  float2 v = make_float2(0.f, 0.f);
+  if (k < 36) {
+    const int pos = k / 9, e = k - 9 * pos;
+    const int d = half == 0 ? (pos == 0 ? 7 : pos == 1 ? 0 : pos == 2 ? 4 : 1) : (pos == 0 ? 5 : pos == 1 ? 2 : pos == 2 ? 6 : 3);
+    v = links[(site * 8 + d) * 9 + e];
+  }
+  padded[i] = v;
 }
 
 static PFN_cuTensorMapEncodeTiled_v12000 encoder() {
@@ -395,9 +453,9 @@ void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, s
   if (!op->links_pad_valid) {
     size_t n4 = (size_t)g.half4;
     for (int p = 0; p < 2; p++) {
-      if (!op->links_pad[p]) CUDA_CHECK(cudaMalloc(&op->links_pad[p], n4 * LINK_ROW_B));
-      size_t n = n4 * (LINK_ROW_F / 4);
-      k_pad_links<<<(unsigned)((n + 255) / 256), 256, 0, g_stream>>>(n4, (const float*)op->links[p], (float*)op->links_pad[p]);
+      if (!op->links_pad[p]) CUDA_CHECK(cudaMalloc(&op->links_pad[p], n4 * 2 * LINK_ROW_B));
+      size_t n = n4 * 2 * 38;
+      k_pad_links<<<(unsigned)((n + 255) / 256), 256, 0, g_stream>>>(n4, (const float2*)op->links[p], (float2*)op->links_pad[p]);
       LAUNCH_CHECK();
     }
     op->links_pad_valid = true;
@@ -438,7 +496,8 @@ void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, s
     encode5(&tmZ, pin, dims, strides, bz, CU_TENSOR_MAP_SWIZZLE_128B);
   }
   {
-    const cuuint64_t dims[5] = {(cuuint64_t)LINK_ROW_F, (cuuint64_t)g.hx, (cuuint64_t)g.L[1], (cuuint64_t)g.L[2], (cuuint64_t)g.L[3]};
+    const cuuint64_t dims[5] = {(cuuint64_t)LINK_ROW_F, (cuuint64_t)g.hx, (cuuint64_t)g.L[1], (cuuint64_t)g.L[2],
+                                (cuuint64_t)2 * g.L[3]};  // last index = half * T + t
     const cuuint64_t row = LINK_ROW_B;
     const cuuint64_t strides[4] = {row, row * g.hx, row * g.hx * g.L[1], row * g.hx * g.L[1] * g.L[2]};
     const cuuint32_t bl[5] = {LINK_ROW_F, TX, TY, TZ, 1};
@@ -446,17 +505,24 @@ void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, s
   }
   static bool configured = false;
   if (!configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(k_dhop_f32_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B));
-    CUDA_CHECK(cudaFuncSetAttribute(k_dhop_f32_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B));
+    CUDA_CHECK(cudaFuncSetAttribute(k_dhop_f32_tma<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B));
+    CUDA_CHECK(cudaFuncSetAttribute(k_dhop_f32_tma<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B));
+    CUDA_CHECK(cudaFuncSetAttribute(k_dhop_f32_tma<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B));
+    CUDA_CHECK(cudaFuncSetAttribute(k_dhop_f32_tma<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B));
     configured = true;
   }
   const int grid_env = env_i("CGPTB_TMA_GRID", 0);
   int grid = grid_env > 0 ? grid_env : sm_count();
   if (grid > G.nitems) grid = G.nitems;
-  if (dag)
-    k_dhop_f32_tma<true><<<grid, NTHREADS, SMEM_B, g_stream>>>(tmC, tmX, tmY, tmZ, tmL, G, pout, out_stride);
+  const int abl = env_i("CGPTB_ABLATE", 0);
+  if (abl == 1)
+    k_dhop_f32_tma<false, 1><<<grid, NTHREADS, SMEM_B, g_stream>>>(tmC, tmX, tmY, tmZ, tmL, G, pout, out_stride);
+  else if (abl == 2)
+    k_dhop_f32_tma<false, 2><<<grid, NTHREADS, SMEM_B, g_stream>>>(tmC, tmX, tmY, tmZ, tmL, G, pout, out_stride);
+  else if (dag)
+    k_dhop_f32_tma<true, 0><<<grid, NTHREADS, SMEM_B, g_stream>>>(tmC, tmX, tmY, tmZ, tmL, G, pout, out_stride);
   else
-    k_dhop_f32_tma<false><<<grid, NTHREADS, SMEM_B, g_stream>>>(tmC, tmX, tmY, tmZ, tmL, G, pout, out_stride);
+    k_dhop_f32_tma<false, 0><<<grid, NTHREADS, SMEM_B, g_stream>>>(tmC, tmX, tmY, tmZ, tmL, G, pout, out_stride);
   LAUNCH_CHECK();
 }
 

@@ -20,7 +20,7 @@ struct cgptb_fermion_operator {
   cgptb::Geom g;
   cgptb_fermion_params p;
   void* links[2] = {0, 0};      // per output parity: [half4][8][9] complex, -c_mu/2 and phases folded in
-  void* links_pad[2] = {0, 0};  // the same links in 592-byte rows for the TMA sweep kernel (dslash_tma.cu), built lazily
+  void* links_pad[2] = {0, 0};  // the same links as [2 halves][site][304 B] for the TMA sweep kernel (dslash_tma.cu), built lazily
   bool links_pad_valid = false;
   bool has_clover = false;
   void* clov[2] = {0, 0};       // per parity: [72][half4] reals

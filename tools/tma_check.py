@@ -38,7 +38,7 @@ def setup(dims, Ls, seed):
 
 
 def apply(qm, src, dag, env):
-    for k in ("CGPTB_NO_TMA", "CGPTB_TMA_GRID", "CGPTB_TMA_TRL"):
+    for k in ("CGPTB_NO_TMA", "CGPTB_TMA_GRID", "CGPTB_TMA_TRL", "CGPTB_ABLATE"):
         os.environ.pop(k, None)
     os.environ.update(env)
     dst = g.vspincolor(qm.F_grid)
@@ -90,20 +90,32 @@ def check():
 
 def timing():
     dims, Ls = bench.DIMS, bench.LS
+    if os.environ.get("DIMS"):
+        dims = [int(x) for x in os.environ["DIMS"].split(".")]
     qm, src = setup(dims, Ls, 5)
     dst = g.vspincolor(qm.F_grid)
     v5 = int(np.prod(dims)) * Ls
     v4 = int(np.prod(dims))
     bytes_per_launch = (v5 // 2) * 48 * 4 + (v4 // 2) * 8 * 18 * 4
+    # VARIANTS="name:K=V,K=V;name2:..." overrides the default sweep
     variants = [("old", {"CGPTB_NO_TMA": "1"})]
-    for trl in os.environ.get("TRLS", "8,16,32,64").split(","):
-        for grid in os.environ.get("GRIDS", "148").split(","):
-            variants.append((f"tma trl={trl} grid={grid}", {"CGPTB_TMA_TRL": trl, "CGPTB_TMA_GRID": grid}))
+    if os.environ.get("VARIANTS"):
+        variants = []
+        for item in os.environ["VARIANTS"].split(";"):
+            name, _, kv = item.partition(":")
+            variants.append((name, dict(x.split("=") for x in kv.split(",") if x)))
+    else:
+        if os.environ.get("ABLATE"):
+            variants += [("tma compute-only", {"CGPTB_ABLATE": "1"}), ("tma memory-only", {"CGPTB_ABLATE": "2"})]
+        for trl in os.environ.get("TRLS", "8,16,32,64").split(","):
+            for grid in os.environ.get("GRIDS", "148").split(","):
+                variants.append((f"tma trl={trl} grid={grid}", {"CGPTB_TMA_TRL": trl, "CGPTB_TMA_GRID": grid}))
     steps = int(os.environ.get("STEPS", "200"))
     for rnd in range(int(os.environ.get("ROUNDS", "2"))):
         for name, env in variants:
-            for k in ("CGPTB_NO_TMA", "CGPTB_TMA_GRID", "CGPTB_TMA_TRL"):
-                os.environ.pop(k, None)
+            for k in list(os.environ):
+                if k.startswith("CGPTB_"):
+                    os.environ.pop(k)
             os.environ.update(env)
             for _ in range(10):
                 qm.Dhop.mat(dst, src)
@@ -114,7 +126,7 @@ def timing():
             ms = cgpt.timer_stop() / steps
             gbs = bytes_per_launch / (ms * 1e-3 / 2) / 1e9
             print(f"TIME {name}: {ms:.4f} ms/step  {gbs:.0f} GB/s  frac {gbs / 6553:.3f}", flush=True)
-    for k in ("CGPTB_NO_TMA", "CGPTB_TMA_GRID", "CGPTB_TMA_TRL"):
+    for k in ("CGPTB_NO_TMA", "CGPTB_TMA_GRID", "CGPTB_TMA_TRL", "CGPTB_ABLATE"):
         os.environ.pop(k, None)
 
 
