@@ -23,6 +23,7 @@
 // restated in lib/gpt/qcd/fermion/reference/wilson_clover.py:182-200.
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include "dslash.cuh"
@@ -63,6 +64,8 @@ struct Geo {
   int tp;  // component-plane stride of the input field in units of time slices
   int p_out;
   int ls;
+  int skip;  // debug (CGPTB_TMA_SKIP): bit 0 x faces, 1 y faces, 2 z faces, 3 links are not loaded (traffic attribution)
+  int hint;  // 0: no L2 hints; 1: z-boundary layers and z faces evict_last; 2: additionally everything else evict_first
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -100,6 +103,16 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
       "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+
+__device__ __forceinline__ void tma_load_5d_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3,
+                                                 int c4, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(policy)
+      : "memory");
+}
+// L2 eviction priorities (createpolicy.fractional encodings, the constants CUTLASS uses for TMA cache hints)
+constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull, L2_EVICT_FIRST = 0x12F0000000000000ull, L2_EVICT_LAST = 0x14F0000000000000ull;
 
 // spinor of one (site, s) from a slice slot: a = byte address of the low 16-byte chunk of plane 0 (swizzle applied)
 __device__ __forceinline__ void lds_spinor(uint32_t a, c32 (&p)[12]) {
@@ -204,7 +217,7 @@ template <bool DAG, int ABL>
 __global__ void __launch_bounds__(NTHREADS, 1)
     k_dhop_f32_tma(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmX,
                    const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmZ,
-                   const __grid_constant__ CUtensorMap tmL, const Geo G, float* __restrict__ out, size_t out_stride) {
+                   const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmM, const Geo G, float* __restrict__ out, size_t out_stride) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t s_bar = sbase + NSLOT * STAGE_B;
@@ -231,6 +244,11 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     // {y-, z+, z-, t+} when the step is over.  Every byte is therefore requested 1.5 steps before it is needed although
     // only two slots fit into shared memory.
     if (lane != 0) return;
+    // optional L2 eviction priorities (CGPTB_TMA_HINT): the z faces of a tile are the z-boundary layers of the tiles above and
+    // below, which are swept one "round" of CTAs earlier or later.  Measured on B200: evict_last on these lines does not
+    // change the DRAM traffic (2.47 vs 2.50 GB read per launch) and evict_first on the rest hurts (2.95 GB): default off.
+    const uint64_t pol_keep = G.hint ? L2_EVICT_LAST : L2_EVICT_NORMAL;
+    const uint64_t pol_rest = G.hint == 2 ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
     uint32_t g = 0;
     for (int item = blockIdx.x; item < G.nitems; item += gridDim.x) {
       const Item it = decode_item(G, item);
@@ -249,18 +267,23 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         const uint32_t dlink = dst + SLOT_B;
         // half A
         mbar_wait(bar + 8 * BAR_EA, ph ^ 1u);
-        if (ABL == 1 || !full_step) {
+        const uint32_t face1 = 3 * (NS / TX) * ROW_B;  // one face, three planes
+        const uint32_t bytesA = ((G.skip & 8) ? 0 : LINK_HALF_B) + ((G.skip & 1) ? 0 : 2 * face1) + ((G.skip & 2) ? 0 : face1);
+        const uint32_t bytesB = ((G.skip & 8) ? 0 : LINK_HALF_B) + ((G.skip & 4) ? 0 : 2 * face1) + ((G.skip & 2) ? 0 : face1);
+        if (ABL == 1 || !full_step || bytesA == 0) {
           mbar_arrive(bar + 8 * BAR_FA);
         } else {
-          mbar_expect_tx(bar + 8 * BAR_FA, (uint32_t)HALF_B);
-          tma_load_5d(dlink, &tmL, bar + 8 * BAR_FA, 0, it.xh0, it.y0, it.z0, tau);
+          mbar_expect_tx(bar + 8 * BAR_FA, bytesA);
+          if (!(G.skip & 8)) tma_load_5d_hint(dlink, &tmL, bar + 8 * BAR_FA, 0, it.xh0, it.y0, it.z0, tau, L2_EVICT_NORMAL);
 #pragma unroll
           for (int k = 0; k < 3; k++) {
             const int tq = k * G.tp + tau;
             const uint32_t d = dst + k * PLANE_B;
-            tma_load_5d(d + OFF_XP, &tmX, bar + 8 * BAR_FA, s0f, xp, it.y0, it.z0, tq);
-            tma_load_5d(d + OFF_XM, &tmX, bar + 8 * BAR_FA, s0f, xm, it.y0, it.z0, tq);
-            tma_load_5d(d + OFF_YP, &tmY, bar + 8 * BAR_FA, s0f, it.xh0, yp, it.z0, tq);
+            if (!(G.skip & 1)) {
+              tma_load_5d_hint(d + OFF_XP, &tmX, bar + 8 * BAR_FA, s0f, xp, it.y0, it.z0, tq, pol_rest);
+              tma_load_5d_hint(d + OFF_XM, &tmX, bar + 8 * BAR_FA, s0f, xm, it.y0, it.z0, tq, pol_rest);
+            }
+            if (!(G.skip & 2)) tma_load_5d_hint(d + OFF_YP, &tmY, bar + 8 * BAR_FA, s0f, it.xh0, yp, it.z0, tq, pol_rest);
           }
         }
         // centre and half B
@@ -271,18 +294,27 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         } else {
           mbar_expect_tx(bar + 8 * BAR_FC, (uint32_t)CENTER_B);
 #pragma unroll
-          for (int k = 0; k < 3; k++)
-            tma_load_5d(dst + k * PLANE_B + OFF_C, &tmC, bar + 8 * BAR_FC, s0f, it.xh0, it.y0, it.z0, k * G.tp + tau);
-          if (full_step) {
-            mbar_expect_tx(bar + 8 * BAR_FB, (uint32_t)HALF_B);
-            tma_load_5d(dlink + LINK_HALF_B, &tmL, bar + 8 * BAR_FB, 0, it.xh0, it.y0, it.z0, G.T + tau);
+          for (int k = 0; k < 3; k++) {
+            // centre box as bottom layer, two middle layers, top layer (rows [z][y][x]: 16 rows per layer)
+            const uint32_t d = dst + k * PLANE_B + OFF_C;
+            const int tq = k * G.tp + tau;
+            tma_load_5d_hint(d, &tmZ, bar + 8 * BAR_FC, s0f, it.xh0, it.y0, it.z0, tq, pol_keep);
+            tma_load_5d_hint(d + 16 * ROW_B, &tmM, bar + 8 * BAR_FC, s0f, it.xh0, it.y0, it.z0 + 1, tq, pol_rest);
+            tma_load_5d_hint(d + 48 * ROW_B, &tmZ, bar + 8 * BAR_FC, s0f, it.xh0, it.y0, it.z0 + 3, tq, pol_keep);
+          }
+          if (full_step && bytesB != 0) {
+            mbar_expect_tx(bar + 8 * BAR_FB, bytesB);
+            if (!(G.skip & 8))
+              tma_load_5d_hint(dlink + LINK_HALF_B, &tmL, bar + 8 * BAR_FB, 0, it.xh0, it.y0, it.z0, G.T + tau, L2_EVICT_NORMAL);
 #pragma unroll
             for (int k = 0; k < 3; k++) {
               const int tq = k * G.tp + tau;
               const uint32_t d = dst + k * PLANE_B;
-              tma_load_5d(d + OFF_YM, &tmY, bar + 8 * BAR_FB, s0f, it.xh0, ym, it.z0, tq);
-              tma_load_5d(d + OFF_ZP, &tmZ, bar + 8 * BAR_FB, s0f, it.xh0, it.y0, zp, tq);
-              tma_load_5d(d + OFF_ZM, &tmZ, bar + 8 * BAR_FB, s0f, it.xh0, it.y0, zm, tq);
+              if (!(G.skip & 2)) tma_load_5d_hint(d + OFF_YM, &tmY, bar + 8 * BAR_FB, s0f, it.xh0, ym, it.z0, tq, pol_rest);
+              if (!(G.skip & 4)) {
+                tma_load_5d_hint(d + OFF_ZP, &tmZ, bar + 8 * BAR_FB, s0f, it.xh0, it.y0, zp, tq, pol_keep);
+                tma_load_5d_hint(d + OFF_ZM, &tmZ, bar + 8 * BAR_FB, s0f, it.xh0, it.y0, zm, tq, pol_keep);
+              }
             }
           } else {
             mbar_arrive(bar + 8 * BAR_FB);
@@ -482,7 +514,9 @@ void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, s
   G.p_out = p_out;
   G.ls = ls;
 
-  CUtensorMap tmC, tmX, tmY, tmZ, tmL;
+  G.hint = env_i("CGPTB_TMA_HINT", 0);
+  G.skip = env_i("CGPTB_TMA_SKIP", 0);
+  CUtensorMap tmC, tmX, tmY, tmZ, tmL, tmM;
   {
     const cuuint64_t dims[5] = {(cuuint64_t)ls * 8, (cuuint64_t)g.hx, (cuuint64_t)g.L[1], (cuuint64_t)g.L[2],
                                 (cuuint64_t)2 * G.tp + g.L[3]};
@@ -494,6 +528,8 @@ void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, s
     encode5(&tmX, pin, dims, strides, bx, CU_TENSOR_MAP_SWIZZLE_128B);
     encode5(&tmY, pin, dims, strides, by, CU_TENSOR_MAP_SWIZZLE_128B);
     encode5(&tmZ, pin, dims, strides, bz, CU_TENSOR_MAP_SWIZZLE_128B);
+    const cuuint32_t bm[5] = {SC * 8, TX, TY, 2, 1};
+    encode5(&tmM, pin, dims, strides, bm, CU_TENSOR_MAP_SWIZZLE_128B);
   }
   {
     const cuuint64_t dims[5] = {(cuuint64_t)LINK_ROW_F, (cuuint64_t)g.hx, (cuuint64_t)g.L[1], (cuuint64_t)g.L[2],
@@ -516,13 +552,13 @@ void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, s
   if (grid > G.nitems) grid = G.nitems;
   const int abl = env_i("CGPTB_ABLATE", 0);
   if (abl == 1)
-    k_dhop_f32_tma<false, 1><<<grid, NTHREADS, SMEM_B, g_stream>>>(tmC, tmX, tmY, tmZ, tmL, G, pout, out_stride);
+    k_dhop_f32_tma<false, 1><<<grid, NTHREADS, SMEM_B, g_stream>>>(tmC, tmX, tmY, tmZ, tmL, tmM, G, pout, out_stride);
   else if (abl == 2)
-    k_dhop_f32_tma<false, 2><<<grid, NTHREADS, SMEM_B, g_stream>>>(tmC, tmX, tmY, tmZ, tmL, G, pout, out_stride);
+    k_dhop_f32_tma<false, 2><<<grid, NTHREADS, SMEM_B, g_stream>>>(tmC, tmX, tmY, tmZ, tmL, tmM, G, pout, out_stride);
   else if (dag)
-    k_dhop_f32_tma<true, 0><<<grid, NTHREADS, SMEM_B, g_stream>>>(tmC, tmX, tmY, tmZ, tmL, G, pout, out_stride);
+    k_dhop_f32_tma<true, 0><<<grid, NTHREADS, SMEM_B, g_stream>>>(tmC, tmX, tmY, tmZ, tmL, tmM, G, pout, out_stride);
   else
-    k_dhop_f32_tma<false, 0><<<grid, NTHREADS, SMEM_B, g_stream>>>(tmC, tmX, tmY, tmZ, tmL, G, pout, out_stride);
+    k_dhop_f32_tma<false, 0><<<grid, NTHREADS, SMEM_B, g_stream>>>(tmC, tmX, tmY, tmZ, tmL, tmM, G, pout, out_stride);
   LAUNCH_CHECK();
 }
 
