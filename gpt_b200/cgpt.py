@@ -83,6 +83,7 @@ SIGNATURES = {
     "cgptb_set_mass_fermion_operator": (c_int, [c_void_p, ctypes.POINTER(fermion_params)]),
     "cgptb_delete_fermion_operator": (c_int, [c_void_p]),
     "cgptb_apply_fermion_operator": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "cgptb_apply_fermion_operator_host": (c_int, [c_void_p, c_int, c_void_p, c_void_p, ctypes.c_size_t]),
     "cgptb_apply_schur_two": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "cgptb_cg_eo2_ne": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_int, _pd, _pi, _pi]),
 }
@@ -376,6 +377,12 @@ def delete_fermion_operator(h):
 def apply_fermion_operator(h, opcode, src, dst):
     """note the (src, dst) order (lib/cgpt/lib/operators.cc:96-107)"""
     _check(_lib_ready().cgptb_apply_fermion_operator(c_void_p(h), int(opcode), c_void_p(src), c_void_p(dst)))
+    return 0.0
+
+
+def apply_fermion_operator_host(h, opcode, src_ptr, dst_ptr, nbytes):
+    """same operator on host buffers (addresses of full fields in GPT order); upload / stencil / download are pipelined"""
+    _check(_lib_ready().cgptb_apply_fermion_operator_host(c_void_p(h), int(opcode), c_void_p(src_ptr), c_void_p(dst_ptr), int(nbytes)))
     return 0.0
 
 

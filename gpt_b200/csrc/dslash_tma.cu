@@ -61,9 +61,11 @@ struct Geo {
   int hx, Ly, Lz, T;
   int nbx, nby, nbz, nchunk;
   int trl, ntr, nitems;
+  int t_begin;  // first time slice of this launch (a launch may cover a slab of the lattice only: hostpipe.cu)
   int tp;  // component-plane stride of the input field in units of time slices
   int p_out;
   int ls;
+  int comm_mask;  // split directions (bit 2: z, bit 3: t): hops that leave the local volume are left to the halo kernels
   int skip;  // debug (CGPTB_TMA_SKIP): bit 0 x faces, 1 y faces, 2 z faces, 3 links are not loaded (traffic attribution)
   int hint;  // 0: no L2 hints; 1: z-boundary layers and z faces evict_last; 2: additionally everything else evict_first
 };
@@ -207,13 +209,15 @@ __device__ __forceinline__ Item decode_item(const Geo& G, int item) {
   it.y0 = (r % G.nby) * TY;
   r /= G.nby;
   it.z0 = (r % G.nbz) * TZ;
-  it.t0 = (r / G.nbz) * G.trl;
+  it.t0 = G.t_begin + (r / G.nbz) * G.trl;
   return it;
 }
 
 // ABL (ablation, CGPTB_ABLATE): 0 production; 1 compute only (no TMA loads, the ring is signalled empty-handed);
 // 2 memory only (all loads and stores, no hop arithmetic)
-template <bool DAG, int ABL>
+// COMM: the lattice is split across GPUs in z and/or t (Geo::comm_mask); off-rank hops are skipped here and added by
+// k_exterior (halo.cu) once the faces have arrived
+template <bool DAG, int ABL, bool COMM>
 __global__ void __launch_bounds__(NTHREADS, 1)
     k_dhop_f32_tma(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmX,
                    const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmZ,
@@ -366,7 +370,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       lds_spinor(sp + a_own, own);
       if (st >= 2) {
         // forward-t hop closes the output of the previous slice
-        if (ABL != 2) hop_math<3, true, DAG>(acc, own, utr, uti);
+        if (ABL != 2 && !(COMM && (G.comm_mask & 8) && tau_prev == G.T - 1)) hop_math<3, true, DAG>(acc, own, utr, uti);
         const size_t site = ((size_t)site0 + (size_t)slice_sites * tau_prev) * G.ls + s;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
@@ -386,7 +390,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       } else if (full_step) {
 #pragma unroll
         for (int k = 0; k < 12; k++) acc[k] = 0ull;
-        {
+        if (!(COMM && (G.comm_mask & 8) && tau == 0)) {
           float wr[9], wi[9];
           lds_link<0>(lrowA, wr, wi);
           hop_math<3, false, DAG>(acc, carry, wr, wi);
@@ -401,8 +405,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       mbar_wait(bar + 8 * BAR_FB, ph);
       if (ABL != 2 && full_step) {
         hop_smem<1, false, DAG, 0>(acc, sp + a_ym, lrowB);
-        hop_smem<2, true, DAG, 1>(acc, sp + a_zp, lrowB);
-        hop_smem<2, false, DAG, 2>(acc, sp + a_zm, lrowB);
+        // lz is uniform within a warp (8 consecutive sites), so these branches do not diverge
+        if (!(COMM && (G.comm_mask & 4) && it.z0 + lz == G.Lz - 1)) hop_smem<2, true, DAG, 1>(acc, sp + a_zp, lrowB);
+        if (!(COMM && (G.comm_mask & 4) && it.z0 + lz == 0)) hop_smem<2, false, DAG, 2>(acc, sp + a_zm, lrowB);
         lds_link<3>(lrowB, utr, uti);
       }
 #pragma unroll
@@ -462,7 +467,8 @@ static int env_i(const char* name, int dflt) {
 // true if the TMA sweep kernel handles this operator / lattice (single GPU, Ls a multiple of 4, extents divisible by
 // the tile); the caller falls back to the kernels of dslash_f32.cu otherwise
 bool dhop_tma_usable(const cgptb_fermion_operator* op) {
-  if (tma::env_i("CGPTB_NO_TMA", 0) || op->prec != CGPTB_SINGLE || op->g.comm_mask) return false;
+  if (tma::env_i("CGPTB_NO_TMA", 0) || op->prec != CGPTB_SINGLE) return false;
+  if (op->g.comm_mask & 3) return false;  // x / y splits: the boundary predicates would diverge inside a warp
   const Geom& g = op->g;
   if (op->ls() % tma::SC) return false;
   if (g.hx % tma::TX || g.L[1] % tma::TY || g.L[2] % tma::TZ || g.L[3] < 2) return false;
@@ -478,7 +484,8 @@ void dhop_tma_release(cgptb_fermion_operator* op) {
 }
 
 void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, size_t in_stride, float* pout, size_t out_stride,
-                       int p_out) {
+                       int p_out, int t_begin, int t_count) {
+  // t_count <= 0: the whole lattice; otherwise output time slices [t_begin, t_begin + t_count) only
   using namespace tma;
   const Geom& g = op->g;
   const int ls = op->ls();
@@ -502,11 +509,17 @@ void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, s
   G.nbz = g.L[2] / TZ;
   G.nchunk = ls / SC;
   const int trl_max = env_i("CGPTB_TMA_TRL", 16);  // time slices per work item: the largest divisor of T below the cap
+  if (t_count <= 0) {
+    t_begin = 0;
+    t_count = G.T;
+  }
+  CGPTB_ASSERT(t_begin >= 0 && t_begin + t_count <= G.T);
   int trl = 1;
-  for (int d = 1; d <= G.T && d <= trl_max; d++)
-    if (G.T % d == 0) trl = d;
+  for (int d = 1; d <= t_count && d <= trl_max; d++)
+    if (t_count % d == 0) trl = d;
   G.trl = trl;
-  G.ntr = G.T / trl;
+  G.ntr = t_count / trl;
+  G.t_begin = t_begin;
   G.nitems = G.nchunk * G.nbx * G.nby * G.nbz * G.ntr;
   const size_t slice_blocks = (size_t)g.hx * g.L[1] * g.L[2] * ls;  // 32-byte blocks per time slice
   CGPTB_ASSERT(in_stride % slice_blocks == 0);
@@ -516,6 +529,7 @@ void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, s
 
   G.hint = env_i("CGPTB_TMA_HINT", 0);
   G.skip = env_i("CGPTB_TMA_SKIP", 0);
+  G.comm_mask = g.comm_mask;
   CUtensorMap tmC, tmX, tmY, tmZ, tmL, tmM;
   {
     const cuuint64_t dims[5] = {(cuuint64_t)ls * 8, (cuuint64_t)g.hx, (cuuint64_t)g.L[1], (cuuint64_t)g.L[2],
@@ -541,24 +555,37 @@ void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, s
   }
   static bool configured = false;
   if (!configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(k_dhop_f32_tma<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B));
-    CUDA_CHECK(cudaFuncSetAttribute(k_dhop_f32_tma<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B));
-    CUDA_CHECK(cudaFuncSetAttribute(k_dhop_f32_tma<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B));
-    CUDA_CHECK(cudaFuncSetAttribute(k_dhop_f32_tma<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B));
+    CUDA_CHECK(cudaFuncSetAttribute(k_dhop_f32_tma<false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B));
+    CUDA_CHECK(cudaFuncSetAttribute(k_dhop_f32_tma<true, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B));
+    CUDA_CHECK(cudaFuncSetAttribute(k_dhop_f32_tma<false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B));
+    CUDA_CHECK(cudaFuncSetAttribute(k_dhop_f32_tma<true, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B));
+    CUDA_CHECK(cudaFuncSetAttribute(k_dhop_f32_tma<false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B));
+    CUDA_CHECK(cudaFuncSetAttribute(k_dhop_f32_tma<false, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B));
     configured = true;
   }
   const int grid_env = env_i("CGPTB_TMA_GRID", 0);
-  int grid = grid_env > 0 ? grid_env : sm_count();
+  // a persistent grid on every SM would keep the NCCL send/recv kernels of the halo exchange from being scheduled until
+  // the stencil is done, so a split lattice leaves a few SMs free for them (CGPTB_TMA_COMM_SMS)
+  int grid = grid_env > 0 ? grid_env : sm_count() - (g.comm_mask ? env_i("CGPTB_TMA_COMM_SMS", 8) : 0);
+  if (grid < 1) grid = 1;
   if (grid > G.nitems) grid = G.nitems;
   const int abl = env_i("CGPTB_ABLATE", 0);
-  if (abl == 1)
-    k_dhop_f32_tma<false, 1><<<grid, NTHREADS, SMEM_B, g_stream>>>(tmC, tmX, tmY, tmZ, tmL, tmM, G, pout, out_stride);
+#define TMA_LAUNCH(DAG_, ABL_, COMM_) \
+  k_dhop_f32_tma<DAG_, ABL_, COMM_><<<grid, NTHREADS, SMEM_B, g_stream>>>(tmC, tmX, tmY, tmZ, tmL, tmM, G, pout, out_stride)
+  if (g.comm_mask) {
+    if (dag)
+      TMA_LAUNCH(true, 0, true);
+    else
+      TMA_LAUNCH(false, 0, true);
+  } else if (abl == 1)
+    TMA_LAUNCH(false, 1, false);
   else if (abl == 2)
-    k_dhop_f32_tma<false, 2><<<grid, NTHREADS, SMEM_B, g_stream>>>(tmC, tmX, tmY, tmZ, tmL, tmM, G, pout, out_stride);
+    TMA_LAUNCH(false, 2, false);
   else if (dag)
-    k_dhop_f32_tma<true, 0><<<grid, NTHREADS, SMEM_B, g_stream>>>(tmC, tmX, tmY, tmZ, tmL, tmM, G, pout, out_stride);
+    TMA_LAUNCH(true, 0, false);
   else
-    k_dhop_f32_tma<false, 0><<<grid, NTHREADS, SMEM_B, g_stream>>>(tmC, tmX, tmY, tmZ, tmL, tmM, G, pout, out_stride);
+    TMA_LAUNCH(false, 0, false);
+#undef TMA_LAUNCH
   LAUNCH_CHECK();
 }
 

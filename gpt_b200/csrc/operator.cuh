@@ -57,7 +57,7 @@ bool op_s_sweep(cgptb_fermion_operator* op, int mode, const cgptb_lattice* in, c
 bool dhop_tma_usable(const cgptb_fermion_operator* op);
 void dhop_tma_release(cgptb_fermion_operator* op);
 void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, size_t in_stride, float* pout, size_t out_stride,
-                       int p_out);
+                       int p_out, int t_begin = 0, int t_count = 0);
 // halo.cu
 void halo_setup(cgptb_fermion_operator* op, const cgptb_lattice* const U[4]);
 void halo_begin(cgptb_fermion_operator* op, bool dag, int p_out, const void* in, size_t in_stride);

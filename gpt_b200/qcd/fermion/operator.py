@@ -50,10 +50,28 @@ class interface:
             self._setup(*self.setup_arguments)
         cgpt.update_fermion_operator(self.obj, params)
 
+    def apply_unary_operator_host(self, opcode, o, i):
+        """o, i: C-contiguous numpy arrays (or anything exposing __array_interface__ / data_ptr) holding full fields in
+        GPT order; equivalent to  lattice[:] = i ; apply ; o[:] = lattice[:]  with the copies overlapped"""
+        assert self.obj is not None
+        return cgpt.apply_fermion_operator_host(self.obj, opcode, _address(i), _address(o), _nbytes(i))
+
     def apply_unary_operator(self, opcode, o, i):
         assert self.obj is not None
         # cgpt adopts Grid's (in, out) order (interface.py:88-91)
         return cgpt.apply_fermion_operator(self.obj, opcode, i.obj, o.obj)
+
+
+def _address(a):
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    return a.__array_interface__["data"][0]
+
+
+def _nbytes(a):
+    if hasattr(a, "data_ptr"):
+        return a.numel() * a.element_size()
+    return a.nbytes
 
 
 class method_registry:
@@ -124,6 +142,9 @@ class fine_operator(g.matrix_operator):
             mo(registry.ExportPhysicalFermionSource, vector_space=(self.vector_space_U, self.vector_space_F))
         )
         self.Dhop = OP(mo(mat=registry.Dhop, adj_mat=registry.DhopDag, vector_space=self.vector_space_F))
+        # host-buffer variant of Dhop: op.Dhop_host(dst_array, src_array)
+        code = 3001 if not daggered else 4001
+        self.Dhop_host = lambda dst, src: self.interface.apply_unary_operator_host(code, dst, src)
 
     # -- variations (base.py:222-262)
     def modified(self, **params):

@@ -154,6 +154,13 @@ int cgptb_delete_fermion_operator(cgptb_fermion_operator* op);
 /* cgpt.apply_fermion_operator(op, opcode, src, dst) -- note (src, dst) order (operators.cc:96-107) */
 int cgptb_apply_fermion_operator(cgptb_fermion_operator* op, int opcode, const cgptb_lattice* src, cgptb_lattice* dst);
 
+/* The same call on HOST buffers (full fields in GPT order, operator precision, nbytes each): replaces the sequence
+   lattice[:] = src (cgpt.lattice_import_view, lib/gpt/core/lattice.py:229-260) ; cgpt.apply_fermion_operator ;
+   dst = lattice[:] (cgpt.lattice_export_view).  For Dhop / DhopDag in single precision the upload, the stencil and
+   the download are pipelined over slabs of time slices (gpt_b200/csrc/hostpipe.cu); every other opcode runs
+   import -> apply -> export.  Synchronous.                                                               */
+int cgptb_apply_fermion_operator_host(cgptb_fermion_operator* op, int opcode, const void* src_host, void* dst_host, size_t nbytes);
+
 /* ---- fused fast paths (same results as the opcode sequences they replace) ---------------------------- */
 /* Mpc / Mpc^dag of schur_complement_two (lib/gpt/algorithms/preconditioner/schur_complement_two.py:87-112):
    o = i - Meooe MooeeInv Meooe MooeeInv i ; tmp = 2 work fields of the same shape                       */

@@ -29,6 +29,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mpi", default=None)
     ap.add_argument("--dims", default="8.8.8.16")
+    ap.add_argument("--Ls", type=int, default=6, help="Ls = 8 routes the single-precision Dslash through the TMA sweep kernel")
     args = ap.parse_args()
 
     import torch
@@ -52,7 +53,7 @@ def main():
 
     rng = oracle_random("mgpu")
     U = qcd.gauge_random(rng, dims, scale=0.7)
-    Ls = 6
+    Ls = args.Ls
     phases = [1.0, -1.0, np.exp(0.4j), -1.0]
     failures = []
 

@@ -19,13 +19,14 @@ def _free_port():
     return p
 
 
+@pytest.mark.parametrize("Ls", [6, 8])  # Ls = 8: fp32 Dslash through the TMA sweep kernel (dslash_tma.cu, COMM instance)
 @pytest.mark.parametrize("mpi", ["1.1.1.2", "1.1.2.1"])
-def test_two_gpu_parity(mpi):
+def test_two_gpu_parity(mpi, Ls):
     import torch
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "mgpu_check.py"), "--mpi", mpi]
+           "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "mgpu_check.py"), "--mpi", mpi, "--Ls", str(Ls)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "MGPU CHECK PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
