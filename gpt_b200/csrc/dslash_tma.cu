@@ -151,7 +151,8 @@ __device__ __forceinline__ void lds_link(uint32_t row, float (&wr)[9], float (&w
 }
 
 // acc += recon( W(^dag) proj psi ), same arithmetic as hop_core of dslash_f32.cu
-template <int MU, bool FWD, bool DAG>
+// INIT: acc = ... instead of acc += ... (first hop of a site: saves clearing the accumulator)
+template <int MU, bool FWD, bool DAG, bool INIT = false>
 __device__ __forceinline__ void hop_math(c32 (&acc)[12], const c32 (&psi)[12], const float (&wr)[9], const float (&wi)[9]) {
   const int SGN = (FWD != DAG) ? -1 : +1;
   typedef Proj<MU, SGN> P;
@@ -181,10 +182,10 @@ __device__ __forceinline__ void hop_math(c32 (&acc)[12], const c32 (&psi)[12], c
   }
 #pragma unroll
   for (int c = 0; c < 3; c++) {
-    acc[c] = add2(acc[c], chi[c]);
-    acc[3 + c] = add2(acc[3 + c], chi[3 + c]);
-    acc[6 + c] = add2(acc[6 + c], times_iph<P::C2>(chi[P::K2 * 3 + c]));
-    acc[9 + c] = add2(acc[9 + c], times_iph<P::C3>(chi[P::K3 * 3 + c]));
+    acc[c] = INIT ? chi[c] : add2(acc[c], chi[c]);
+    acc[3 + c] = INIT ? chi[3 + c] : add2(acc[3 + c], chi[3 + c]);
+    acc[6 + c] = add2(INIT ? 0ull : acc[6 + c], times_iph<P::C2>(chi[P::K2 * 3 + c]));
+    acc[9 + c] = add2(INIT ? 0ull : acc[9 + c], times_iph<P::C3>(chi[P::K3 * 3 + c]));
   }
 }
 
@@ -388,12 +389,13 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 #pragma unroll
         for (int k = 0; k < 12; k++) acc[k] = own[k];
       } else if (full_step) {
+        if (COMM && (G.comm_mask & 8) && tau == 0) {
 #pragma unroll
-        for (int k = 0; k < 12; k++) acc[k] = 0ull;
-        if (!(COMM && (G.comm_mask & 8) && tau == 0)) {
+          for (int k = 0; k < 12; k++) acc[k] = 0ull;
+        } else {
           float wr[9], wi[9];
           lds_link<0>(lrowA, wr, wi);
-          hop_math<3, false, DAG>(acc, carry, wr, wi);
+          hop_math<3, false, DAG, true>(acc, carry, wr, wi);
         }
         hop_smem<0, true, DAG, 1>(acc, sp + a_xp, lrowA);
         hop_smem<0, false, DAG, 2>(acc, sp + a_xm, lrowA);
