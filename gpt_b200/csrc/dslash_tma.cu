@@ -8,7 +8,8 @@
 //   * work item = (4x4x4 tile of checkerboard sites in (x/2, y, z)) x (chunk of SC = 4 fifth-dimension slices) x (range
 //     of TRL time slices); a persistent CTA (one per SM) walks its items and sweeps each along t;
 //   * per time slice the producer loads, for each of the three 32-byte component planes, the centre box of the tile
-//     (64 sites) and its six (x/2, y, z) faces (16 sites each) -- 21 box loads with the 128-byte swizzle, each shared
+//     (64 sites, as bottom / middle / top z layers) and its six (x/2, y, z) faces (16 sites each) -- 27 box loads with the
+//     128-byte swizzle, each shared
 //     memory row being the 4 x 32 B of one site -- plus the tile's 64 x 8 links (two boxes of four links each):
 //     2.5 spinor loads per output site instead of 8, all address arithmetic done by the TMA unit;
 //   * only two stages (2 x 98 KB) fit into shared memory, so each stage is handed back in two halves (after the fourth
@@ -220,9 +221,9 @@ __device__ __forceinline__ Item decode_item(const Geo& G, int item) {
 // k_exterior (halo.cu) once the faces have arrived
 template <bool DAG, int ABL, bool COMM>
 __global__ void __launch_bounds__(NTHREADS, 1)
-    k_dhop_f32_tma(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmX,
-                   const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmZ,
-                   const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmM, const Geo G, float* __restrict__ out, size_t out_stride) {
+    k_dhop_f32_tma(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+                   const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmM,
+                   const __grid_constant__ CUtensorMap tmL, const Geo G, float* __restrict__ out, size_t out_stride) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t s_bar = sbase + NSLOT * STAGE_B;
@@ -532,15 +533,14 @@ void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, s
   G.hint = env_i("CGPTB_TMA_HINT", 0);
   G.skip = env_i("CGPTB_TMA_SKIP", 0);
   G.comm_mask = g.comm_mask;
-  CUtensorMap tmC, tmX, tmY, tmZ, tmL, tmM;
+  // box shapes: one x column, one y row, one z layer (also the bottom / top layer of the centre box), two z layers (its middle)
+  CUtensorMap tmX, tmY, tmZ, tmM, tmL;
   {
     const cuuint64_t dims[5] = {(cuuint64_t)ls * 8, (cuuint64_t)g.hx, (cuuint64_t)g.L[1], (cuuint64_t)g.L[2],
                                 (cuuint64_t)2 * G.tp + g.L[3]};
     const cuuint64_t row = (cuuint64_t)ls * 32;
     const cuuint64_t strides[4] = {row, row * g.hx, row * g.hx * g.L[1], row * g.hx * g.L[1] * g.L[2]};
-    const cuuint32_t bc[5] = {SC * 8, TX, TY, TZ, 1}, bx[5] = {SC * 8, 1, TY, TZ, 1}, by[5] = {SC * 8, TX, 1, TZ, 1},
-                     bz[5] = {SC * 8, TX, TY, 1, 1};
-    encode5(&tmC, pin, dims, strides, bc, CU_TENSOR_MAP_SWIZZLE_128B);
+    const cuuint32_t bx[5] = {SC * 8, 1, TY, TZ, 1}, by[5] = {SC * 8, TX, 1, TZ, 1}, bz[5] = {SC * 8, TX, TY, 1, 1};
     encode5(&tmX, pin, dims, strides, bx, CU_TENSOR_MAP_SWIZZLE_128B);
     encode5(&tmY, pin, dims, strides, by, CU_TENSOR_MAP_SWIZZLE_128B);
     encode5(&tmZ, pin, dims, strides, bz, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -573,7 +573,7 @@ void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, s
   if (grid > G.nitems) grid = G.nitems;
   const int abl = env_i("CGPTB_ABLATE", 0);
 #define TMA_LAUNCH(DAG_, ABL_, COMM_) \
-  k_dhop_f32_tma<DAG_, ABL_, COMM_><<<grid, NTHREADS, SMEM_B, g_stream>>>(tmC, tmX, tmY, tmZ, tmL, tmM, G, pout, out_stride)
+  k_dhop_f32_tma<DAG_, ABL_, COMM_><<<grid, NTHREADS, SMEM_B, g_stream>>>(tmX, tmY, tmZ, tmM, tmL, G, pout, out_stride)
   if (g.comm_mask) {
     if (dag)
       TMA_LAUNCH(true, 0, true);

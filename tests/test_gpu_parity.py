@@ -423,3 +423,41 @@ def test_dhop_host_buffers_double(g, fields):
     out = np.zeros_like(s5)
     m.Dhop_host(out, s5)
     assert rel(out, mo.Dhop(s5)) < TOL["double"]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# TMA sweep kernel (dslash_tma.cu): asymmetric lattices, several Ls, work schedules that put many items and
+# time ranges on one CTA; against the oracle and against the L1 kernels (CGPTB_NO_TMA)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dims,Ls", [([16, 8, 12, 8], 8), ([8, 12, 8, 6], 4), ([8, 8, 8, 16], 16)])
+def test_tma_sweep_kernel_geometries(g, dims, Ls, monkeypatch):
+    rng = oracle_random("tma" + str(dims))
+    U = qcd.gauge_random(rng, dims, scale=0.8)
+    params = dict(mass=0.08, M5=1.8, b=1.5, c=0.5, Ls=Ls, boundary_phases=[1.0, -1.0, np.exp(0.3j), -1.0])
+    grid = g.grid(dims, g.single)
+    m = g.qcd.fermion.mobius(to_links(g, grid, U), dict(params))
+    mo = qcd.mobius([u.astype(np.complex64) for u in U], **params)
+    s5 = rng.cnormal([Ls] + dims, (4, 3)).astype(np.complex64)
+    src = to_spinor(g, m.F_grid, s5)
+    for dag in (False, True):
+        ref = mo.Dhop(s5, dag=dag)
+        op = m.Dhop.adj() if dag else m.Dhop
+        monkeypatch.setenv("CGPTB_NO_TMA", "1")
+        l1 = from_spinor(g(op * src), s5)
+        monkeypatch.delenv("CGPTB_NO_TMA")
+        assert rel(l1, ref) < TOL["single"]
+        for env in ({}, {"CGPTB_TMA_GRID": "1", "CGPTB_TMA_TRL": "2"}, {"CGPTB_TMA_GRID": "5", "CGPTB_TMA_TRL": "4"},
+                    {"CGPTB_TMA_GRID": "3", "CGPTB_TMA_TRL": "1"}):
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            got = from_spinor(g(op * src), s5)
+            for k in env:
+                monkeypatch.delenv(k)
+            assert rel(got, ref) < TOL["single"], (dag, env)
+            assert rel(got, l1) < 2e-6, (dag, env)  # only the summation order of the eight hops differs
+    # checkerboarded entry (DhopEO on half fields: component planes of half the stride)
+    e = qcd.eo_ops(mo)
+    for cb in (g.even, g.odd):
+        half = to_spinor(g, m.F_grid_eo, s5, cb)
+        out = from_spinor(g(m.DhopEO * half), s5)
+        assert rel(out, e.proj(mo.Dhop(e.proj(s5, cb.tag)), 1 - cb.tag)) < TOL["single"]
