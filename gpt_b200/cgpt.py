@@ -52,6 +52,14 @@ SIGNATURES = {
     "cgptb_comm_finalize": (c_int, []),
     "cgptb_comm_info": (c_int, [_pi, _pi, _pi, _pi]),
     "cgptb_comm_globalsum": (c_int, [_pd, c_int]),
+    "cgptb_gauge_plaquette": (c_int, [ctypes.POINTER(c_void_p), _pd]),
+    "cgptb_create_random": (c_int, [ctypes.POINTER(c_void_p), ctypes.c_char_p, ctypes.c_char_p]),
+    "cgptb_delete_random": (c_int, [c_void_p]),
+    "cgptb_random_sample_scalar": (c_int, [c_void_p, c_int, c_double, c_double, _pd]),
+    "cgptb_random_sample_host": (c_int, [c_void_p, ctypes.c_uint64, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int),
+                                         ctypes.POINTER(c_int), c_int, c_int, c_double, c_double, _pd]),
+    "cgptb_random_sample": (c_int, [c_void_p, ctypes.c_uint64, c_void_p, c_int, c_double, c_double]),
+    "cgptb_random_su3_links": (c_int, [c_void_p, ctypes.c_uint64, ctypes.POINTER(c_void_p), c_double]),
     "cgptb_create_lattice": (c_int, [_pp, _pi, c_int, c_int, c_int, c_int]),
     "cgptb_create_lattice_view": (c_int, [_pp, _pi, c_int, c_int, c_int, c_int, c_void_p]),
     "cgptb_delete_lattice": (c_int, [c_void_p]),
@@ -378,6 +386,70 @@ def apply_fermion_operator(h, opcode, src, dst):
     """note the (src, dst) order (lib/cgpt/lib/operators.cc:96-107)"""
     _check(_lib_ready().cgptb_apply_fermion_operator(c_void_p(h), int(opcode), c_void_p(src), c_void_p(dst)))
     return 0.0
+
+
+# ---- random numbers (lib/cgpt/lib/random.cc:38-101) -------------------------------------------------------------
+DISTRIBUTIONS = {"normal": 0, "cnormal": 1, "uniform_real": 2, "uniform_int": 3, "zn": 4}
+
+
+def _dist_params(p):
+    d = p["distribution"]
+    if d in ("normal", "cnormal"):
+        return DISTRIBUTIONS[d], float(p["mu"]), float(p["sigma"])
+    if d in ("uniform_real", "uniform_int"):
+        return DISTRIBUTIONS[d], float(p["min"]), float(p["max"])
+    if d == "zn":
+        return DISTRIBUTIONS[d], float(p["n"]), 0.0
+    raise RuntimeError(f"Unknown distribution: {d}")
+
+
+def create_random(engine, seed):
+    """the library itself needs no device for this: the generators are host code"""
+    h = c_void_p()
+    _check(library().cgptb_create_random(ctypes.byref(h), engine.encode(), seed.encode()))
+    return h.value
+
+
+def delete_random(h):
+    if _lib is not None:
+        _lib.cgptb_delete_random(c_void_p(h))
+
+
+def random_sample_scalar(h, p):
+    out = (c_double * 2)()
+    d, p0, p1 = _dist_params(p)
+    _check(library().cgptb_random_sample_scalar(c_void_p(h), d, p0, p1, out))
+    return complex(out[0], out[1])
+
+
+def random_sample_host(h, grid_key, ldims, gdims, lstart, nel, p):
+    """numpy array [sites, nel] complex128 in GPT order (dimension 0 fastest); no device needed"""
+    import numpy as np
+
+    nd = len(ldims)
+    out = np.empty((int(np.prod(ldims)), nel), dtype=np.complex128)
+    d, p0, p1 = _dist_params(p)
+    arr = lambda v: (c_int * nd)(*[int(x) for x in v])  # noqa: E731
+    _check(library().cgptb_random_sample_host(c_void_p(h), int(grid_key), nd, arr(ldims), arr(gdims), arr(lstart), int(nel), d, p0, p1,
+                                              out.ctypes.data_as(_pd)))
+    return out
+
+
+def random_sample(h, grid_key, lattice, p):
+    d, p0, p1 = _dist_params(p)
+    _check(_lib_ready().cgptb_random_sample(c_void_p(h), int(grid_key), c_void_p(lattice), d, p0, p1))
+
+
+def random_su3_links(h, grid_key, U, scale):
+    arr = (c_void_p * 4)(*U)
+    _check(_lib_ready().cgptb_random_su3_links(c_void_p(h), int(grid_key), arr, float(scale)))
+
+
+def gauge_plaquette(U):
+    """(plaquette, link trace) of four link lattices"""
+    out = (c_double * 2)()
+    _check(_lib_ready().cgptb_gauge_plaquette((c_void_p * 4)(*U), out))
+    return out[0], out[1]
 
 
 def apply_fermion_operator_host(h, opcode, src_ptr, dst_ptr, nbytes):

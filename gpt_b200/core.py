@@ -74,6 +74,8 @@ class redblack:
 class grid:
     """g.grid(fdimensions, precision, cb=full): 4d [x,y,z,t] or 5d [s,x,y,z,t] (s never checkerboarded)."""
 
+    _serial = 0
+
     def __init__(self, fdimensions, precision, cb=None, parent=None, mpi=None):
         self.fdimensions = [int(x) for x in fdimensions]
         self.gdimensions = list(self.fdimensions)
@@ -94,6 +96,9 @@ class grid:
         self.ldimensions = self.fdimensions[:-4] + parallel.local_dims(self.fdimensions[-4:], mpi4)
         self.gsites = int(np.prod(self.fdimensions))
         self.obj = self  # cgpt grid handles are not needed: a lattice carries its geometry
+        # every grid OBJECT owns its set of parallel generators inside a g.random (engine.h:82-99)
+        grid._serial += 1
+        self.serial = grid._serial
 
     @property
     def dims4(self):

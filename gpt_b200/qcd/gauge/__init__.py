@@ -1,4 +1,4 @@
-"""g.qcd.gauge.{unit, random} (lib/gpt/qcd/gauge/create.py:24-80)"""
+"""g.qcd.gauge.{unit, random} (lib/gpt/qcd/gauge/create.py:24-80), g.qcd.gauge.plaquette (lib/gpt/qcd/gauge/stencil/plaquette.py:23-44)"""
 import numpy as np
 
 import gpt_b200 as g
@@ -29,3 +29,13 @@ def from_numpy(grid, arrays):
 def random(grid, rng, scale=1.0):
     """g.qcd.gauge.random(grid, rng, scale): needs a gpt_b200.random engine"""
     return rng.element_links(grid, scale)
+
+
+def plaquette(U):
+    """average of Re tr P_{mu nu} / Nc over the six planes and all sites, computed on the device"""
+    return g.cgpt.gauge_plaquette([u.obj for u in U])[0]
+
+
+def link_trace(U):
+    """average of Re tr U_mu / Nc (the LINK_TRACE of a NERSC header)"""
+    return g.cgpt.gauge_plaquette([u.obj for u in U])[1]

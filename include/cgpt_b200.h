@@ -161,6 +161,30 @@ int cgptb_apply_fermion_operator(cgptb_fermion_operator* op, int opcode, const c
    import -> apply -> export.  Synchronous.                                                               */
 int cgptb_apply_fermion_operator_host(cgptb_fermion_operator* op, int opcode, const void* src_host, void* dst_host, size_t nbytes);
 
+/* ---- random numbers: cgpt.create_random(engine, seed) / cgpt.random_sample(rng, params) / cgpt.delete_random
+   (lib/cgpt/lib/random.cc:38-101, random/engine.h:64-125).  Same streams as the reference: RANLUX24 lanes seeded by
+   SHA-256, one generator per 2^4 block of sites, values drawn in double.  engine: "vectorized_ranlux24_389_64" (default
+   of gpt.random) or "vectorized_ranlux24_24_64".  grid_key tells grid objects apart: the reference keeps one set of
+   generators per (rng, grid object), so two grids of equal shape each restart from the seed.                        */
+typedef struct cgptb_random cgptb_random;
+enum { CGPTB_DIST_NORMAL = 0, CGPTB_DIST_CNORMAL = 1, CGPTB_DIST_UNIFORM_REAL = 2, CGPTB_DIST_UNIFORM_INT = 3, CGPTB_DIST_ZN = 4 };
+int cgptb_create_random(cgptb_random** out, const char* engine, const char* seed);
+int cgptb_delete_random(cgptb_random* r);
+/* p0, p1 = (mu, sigma) for normal / cnormal, (min, max) for uniform_real / uniform_int, (n, -) for zn */
+int cgptb_random_sample_scalar(cgptb_random* r, int dist, double p0, double p1, double out[2]);
+/* fill a host array out[site][nel][re,im] (site lexicographic, dimension 0 fastest; nd <= 5, dimension 0 of a 5d grid
+   is the unblocked fifth dimension); ldims / gdims / lstart: local extents, global extents, global origin of the local block */
+int cgptb_random_sample_host(cgptb_random* r, uint64_t grid_key, int nd, const int* ldims, const int* gdims, const int* lstart,
+                             int nel, int dist, double p0, double p1, double* out);
+/* the same into a (full) lattice */
+int cgptb_random_sample(cgptb_random* r, uint64_t grid_key, cgptb_lattice* l, int dist, double p0, double p1);
+/* g.qcd.gauge.random(grid, rng, scale) (lib/gpt/qcd/gauge/create.py:66-71): U_mu = exp(i scale sum_a u_a T_a), u_a ~ U[-1/2,1/2) */
+int cgptb_random_su3_links(cgptb_random* r, uint64_t grid_key, cgptb_lattice* const U[4], double scale);
+
+/* g.qcd.gauge.plaquette(U) (lib/gpt/qcd/gauge/stencil/plaquette.py:23-44) and the NERSC link trace (lib/gpt/core/io/nersc_io.py:238-247):
+   out[0] = <Re tr P_{mu nu}> / Nc over the six planes, out[1] = <Re tr U_mu> / Nc over the four directions */
+int cgptb_gauge_plaquette(const cgptb_lattice* const U[4], double out[2]);
+
 /* ---- fused fast paths (same results as the opcode sequences they replace) ---------------------------- */
 /* Mpc / Mpc^dag of schur_complement_two (lib/gpt/algorithms/preconditioner/schur_complement_two.py:87-112):
    o = i - Meooe MooeeInv Meooe MooeeInv i ; tmp = 2 work fields of the same shape                       */

@@ -461,3 +461,57 @@ def test_tma_sweep_kernel_geometries(g, dims, Ls, monkeypatch):
         half = to_spinor(g, m.F_grid_eo, s5, cb)
         out = from_spinor(g(m.DhopEO * half), s5)
         assert rel(out, e.proj(mo.Dhop(e.proj(s5, cb.tag)), 1 - cb.tag)) < TOL["single"]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# g.random / g.qcd.gauge.random / g.qcd.gauge.plaquette of the product against the reference's known answers
+# (/root/reference/tests/random/simple.py:18-31) and the oracle
+# ---------------------------------------------------------------------------------------------------------
+def test_product_gauge_random_and_plaquette_kat(g):
+    rng = g.random("block_seed_string_13")
+    orng = oracle_random("block_seed_string_13")
+    for dims, precision, ref, scale, tol in [
+        ([8, 4, 4, 4], "double", -0.00014108397456619623, 10, 1e-14),
+        ([8, 4, 4, 4], "single", -0.00014108397456619623, 10, 1e-7),
+        ([8, 8, 4, 8], "double", 0.38723058417632267, 2, 1e-14),
+    ]:
+        grid = g.grid(dims, prec_of(g, precision))
+        U = g.qcd.gauge.random(grid, rng, scale=scale)
+        P = g.qcd.gauge.plaquette(U)
+        assert abs(P - ref) < tol, (dims, precision, P)
+        Uo = qcd.gauge_random(orng, dims, scale=scale, precision=precision)
+        for u, uo in zip(U, Uo):
+            assert rel(u[:], sites(uo, 2)) < (1e-13 if precision == "double" else 1e-6)
+        assert abs(P - qcd.plaquette(Uo)) < tol
+        lt = sum(np.trace(uo, axis1=-2, axis2=-1).real.mean() for uo in Uo) / 12.0
+        assert abs(g.qcd.gauge.link_trace(U) - lt) < tol
+
+
+@pytest.mark.parametrize("precision", ["double", "single"])
+def test_product_rng_lattices(g, precision):
+    """rng.cnormal / normal / uniform_real into 4d and 5d lattices == oracle stream (draw order as in
+    tests/qcd/fermion_operators.py:849-884: U, then sources on F_grid and U_grid)"""
+    dims = [8, 8, 8, 16]
+    p = prec_of(g, precision)
+    grid = g.grid(dims, p)
+    rng = g.random("finger_print")
+    orng = oracle_random("finger_print")
+    tag = None if precision == "double" else precision
+    U = g.qcd.gauge.random(grid, rng)
+    Uo = qcd.gauge_random(orng, dims, precision=precision)
+    tol = 1e-13 if precision == "double" else 1e-6
+    for u, uo in zip(U, Uo):
+        assert rel(u[:], sites(uo, 2)) < tol
+    grid5 = grid.inserted_dimension(0, 12)
+    src5 = rng.cnormal(g.vspincolor(grid5))
+    dst5 = rng.cnormal(g.vspincolor(grid5))
+    src4 = rng.cnormal(g.vspincolor(grid))
+    d5 = [12] + dims
+    assert rel(src5[:], sites(orng.cnormal(d5, (4, 3), grid_tag=tag), 2)) < tol
+    assert rel(dst5[:], sites(orng.cnormal(d5, (4, 3), grid_tag=tag), 2)) < tol
+    assert rel(src4[:], sites(orng.cnormal(dims, (4, 3), grid_tag=tag), 2)) < tol
+    if precision == "double":
+        # the reference's Moebius fingerprint from the product's own random fields (fermion_operators.py:427-442)
+        m = g.qcd.fermion.mobius(U, dict(MOBIUS))
+        X = g.inner_product(dst5, g(m * src5))
+        assert abs(X - (-8693.09425573421 - 4130.7793316734915j)) / abs(X) < 1e-13
