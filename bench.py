@@ -144,18 +144,15 @@ def run_native(args):
     dims = list(DIMS)  # local extents; weak scaling: the global lattice grows with the processor grid
     gdims = [d * m for d, m in zip(dims, mpi)]
     grid = g.grid(gdims, g.single)
-    U_t, src_t = synthetic_fields_device(torch, dims, LS, 1234 + rank)
-    U = []
-    for mu in range(4):
-        u = g.mcolor(grid)
-        cgpt.lattice_import_device(u.obj, U_t[mu].data_ptr(), U_t[mu].numel() * 8)
-        U.append(u)
-    cgpt.accelerator_barrier()
+    # inputs exactly as /root/reference/benchmarks/dslash.py:10-49: GPT's own generator (fast engine), SU(3) links
+    # exp(i 0.5 sum_a u_a T_a), complex normal source; every rank draws its block of the global lattice
+    rng = g.random("benchmark", "vectorized_ranlux24_24_64")
+    U = g.qcd.gauge.random(grid, rng, scale=0.5)
     qm = g.qcd.fermion.mobius(U, dict(MOBIUS))
-    del U_t
     src = g.vspincolor(qm.F_grid)
     dst = g.vspincolor(qm.F_grid)
-    cgpt.lattice_import_device(src.obj, src_t.data_ptr(), src_t.numel() * 8)
+    rng.cnormal(src)
+    del rng
     cgpt.accelerator_barrier()
 
     v5 = int(np.prod(dims)) * LS
@@ -205,11 +202,10 @@ def run_native(args):
     # end to end through the public API with HOST buffers (pinned): import -> Dhop -> export
     e2e = None
     if not args.no_e2e:
-        nbytes = src_t.numel() * 8
+        nbytes = v5 * 12 * 8
         h_in = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
         h_out = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
-        h_in.copy_(src_t.view(torch.uint8).reshape(-1))
-        del src_t
+        cgpt.lattice_export_ptr(src.obj, h_in.data_ptr(), nbytes)
         n_e2e = max(3, min(args.steps, 10))
         # the public host-buffer call: op.Dhop_host(dst, src) == lattice[:] = src ; dst_l = Dhop * src_l ; dst = dst_l[:]
         # with upload / stencil / download pipelined over slabs of time slices (gpt_b200/csrc/hostpipe.cu)
@@ -265,7 +261,7 @@ def run_native(args):
         out = {
             "metric": "mobius_dwf_dslash_gflops", "value": gflops, "unit": "GFlop/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (g.random(\"benchmark\", ranlux24_24) links scale 0.5 + cnormal source, as benchmarks/dslash.py)",
             "config": {"workload": "Mobius DWF Dhop 32^3x64 Ls=12 single per GPU (BASELINE.json configs[2]; T-split, global T=64*n_gpus)",
                        "local_dims": dims, "Ls": LS, "cache": "inputs (2.4 GB field + 0.6 GB links) larger than L2, no flush needed",
                        "global_dims": gdims, "parallelism": "mpi " + ".".join(str(m) for m in mpi) + " (x.y.z.t), halo exchange NCCL send/recv overlapped with the interior stencil"},

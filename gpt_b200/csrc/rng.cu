@@ -309,7 +309,8 @@ static GridRng& grid_rng(cgptb_random* r, uint64_t key, int nd, const int* ldims
 
 // out[site][e] (re, im), site = lexicographic local index with dimension 0 fastest; every block generator fills the
 // sites of its block in lexicographic order (dimension 0 fastest), the nel elements of a site one after the other
-static void sample_grid(GridRng& G, int nel, int dist, double p0, double p1, double* out) {
+template <typename TO>
+static void sample_grid(GridRng& G, int nel, int dist, double p0, double p1, TO* out) {
   const int nd = G.nd;
   const long blocks = (long)G.gen.size();
 #pragma omp parallel for schedule(dynamic, 16)
@@ -333,8 +334,13 @@ static void sample_grid(GridRng& G, int nel, int dist, double p0, double p1, dou
         flat += (long)c * stride;
         stride *= G.ldims[j];
       }
-      double* o = out + (size_t)flat * nel * 2;
-      for (int e = 0; e < nel; e++) gen.sample(dist, p0, p1, o[2 * e], o[2 * e + 1]);
+      TO* o = out + (size_t)flat * nel * 2;
+      for (int e = 0; e < nel; e++) {
+        double re, im;
+        gen.sample(dist, p0, p1, re, im);  // always drawn in double, then cast (engine.h:104-105)
+        o[2 * e] = (TO)re;
+        o[2 * e + 1] = (TO)im;
+      }
     }
   }
 }
@@ -453,9 +459,17 @@ int cgptb_random_sample(cgptb_random* r, uint64_t grid_key, cgptb_lattice* l, in
   int nd, ldims[5], gdims[5], lstart[5];
   lattice_geometry(l, nd, ldims, gdims, lstart);
   GridRng& G = grid_rng(r, grid_key, nd, ldims, gdims, lstart);
-  std::vector<double> v(l->sites * (size_t)l->otype * 2);
-  sample_grid(G, l->otype, dist, p0, p1, v.data());
-  import_doubles(l, v);
+  const size_t n = l->sites * (size_t)l->otype * 2;
+  if (l->prec == CGPTB_DOUBLE) {
+    std::vector<double> v(n);
+    sample_grid(G, l->otype, dist, p0, p1, v.data());
+    import_doubles(l, v);
+  } else {
+    std::vector<float> v(n);
+    sample_grid(G, l->otype, dist, p0, p1, v.data());
+    if (cgptb_lattice_import(l, v.data(), n * sizeof(float))) throw Error{g_error};
+    CUDA_CHECK(cudaStreamSynchronize(g_stream));  // the staging copy reads the host vector
+  }
   CGPTB_API_END
 }
 
