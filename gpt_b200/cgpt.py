@@ -53,6 +53,7 @@ SIGNATURES = {
     "cgptb_comm_info": (c_int, [_pi, _pi, _pi, _pi]),
     "cgptb_comm_globalsum": (c_int, [_pd, c_int]),
     "cgptb_gauge_plaquette": (c_int, [ctypes.POINTER(c_void_p), _pd]),
+    "cgptb_nersc_munge": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(ctypes.c_uint)]),
     "cgptb_create_random": (c_int, [ctypes.POINTER(c_void_p), ctypes.c_char_p, ctypes.c_char_p]),
     "cgptb_delete_random": (c_int, [c_void_p]),
     "cgptb_random_sample_scalar": (c_int, [c_void_p, c_int, c_double, c_double, _pd]),
@@ -450,6 +451,14 @@ def gauge_plaquette(U):
     out = (c_double * 2)()
     _check(_lib_ready().cgptb_gauge_plaquette((c_void_p * 4)(*U), out))
     return out[0], out[1]
+
+
+def nersc_munge(raw, float_size, big_endian, rows, U):
+    """raw: C-contiguous uint8 numpy array with the data part of a NERSC file; returns the checksum"""
+    cs = ctypes.c_uint(0)
+    _check(_lib_ready().cgptb_nersc_munge(c_void_p(raw.ctypes.data), int(raw.nbytes), int(float_size), 1 if big_endian else 0, int(rows),
+                                          (c_void_p * 4)(*U), ctypes.byref(cs)))
+    return cs.value
 
 
 def apply_fermion_operator_host(h, opcode, src_ptr, dst_ptr, nbytes):

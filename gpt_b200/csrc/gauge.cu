@@ -118,3 +118,114 @@ int cgptb_gauge_plaquette(const cgptb_lattice* const U[4], double out[2]) {
   CGPTB_API_END
 }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// NERSC gauge configurations: the byte work between the file and the link lattices, on the device.
+// File order (lib/gpt/core/io/nersc_io.py:146-199): sites lexicographic with x fastest, per site the four directions,
+// per link 2 x 3 (4D_SU3_GAUGE, third row = conj(row0 x row1), lib/cgpt/lib/munge.h:21-39) or 3 x 3 complex numbers,
+// IEEE32/64, big or little endian.  Checksum = sum of the data as native-endian 32-bit words
+// (lib/cgpt/lib/checksums/nersc.h:19-33).  One thread per (site, direction).
+// ---------------------------------------------------------------------------------------------------------
+namespace cgptb {
+
+__device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+
+template <typename TF, typename TL>
+__global__ void __launch_bounds__(128) k_nersc_munge(Geom g, size_t nsites, int big_endian, int rows, const unsigned char* __restrict__ raw,
+                                                     TL* U0, TL* U1, TL* U2, TL* U3, unsigned int* __restrict__ checksum) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // = lex site * 4 + mu
+  uint32_t cs = 0;
+  if (idx < nsites * 4) {
+    const int mu = (int)(idx & 3);
+    size_t lex = idx >> 2;
+    const int x = (int)(lex % g.L[0]);
+    lex /= g.L[0];
+    const int y = (int)(lex % g.L[1]);
+    lex /= g.L[1];
+    const int z = (int)(lex % g.L[2]);
+    const int t = (int)(lex / g.L[2]);
+    const int nval = rows * 3 * 2;
+    const unsigned char* p = raw + idx * (size_t)nval * sizeof(TF);
+    double m[18];
+    for (int k = 0; k < nval; k++) {
+      if (sizeof(TF) == 4) {
+        uint32_t w = reinterpret_cast<const uint32_t*>(p)[k];
+        if (big_endian) w = bswap32(w);
+        cs += w;
+        m[k] = (double)__uint_as_float(w);
+      } else {
+        uint32_t a = reinterpret_cast<const uint32_t*>(p)[2 * k], b = reinterpret_cast<const uint32_t*>(p)[2 * k + 1];
+        uint32_t lo = a, hi = b;
+        if (big_endian) {
+          lo = bswap32(b);
+          hi = bswap32(a);
+        }
+        cs += lo;
+        cs += hi;
+        m[k] = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+      }
+    }
+    if (rows == 2) {
+      // third row = conj(row0 x row1)
+      for (int c = 0; c < 3; c++) {
+        const int c1 = (c + 1) % 3, c2 = (c + 2) % 3;
+        const double ar = m[2 * c1], ai = m[2 * c1 + 1], br = m[2 * (3 + c2)], bi = m[2 * (3 + c2) + 1];
+        const double cr = m[2 * c2], ci = m[2 * c2 + 1], dr = m[2 * (3 + c1)], di = m[2 * (3 + c1) + 1];
+        const double re = (ar * br - ai * bi) - (cr * dr - ci * di);
+        const double im = (ar * bi + ai * br) - (cr * di + ci * dr);
+        m[2 * (6 + c)] = re;
+        m[2 * (6 + c) + 1] = -im;
+      }
+    }
+    const int par = (x + y + z + t) & 1;
+    const size_t site = (size_t)par * g.half4 + cb_index(g, x, y, z, t);
+    TL* U = mu == 0 ? U0 : (mu == 1 ? U1 : (mu == 2 ? U2 : U3));
+    for (int k = 0; k < 9; k++) {
+      const size_t o = elem_offset<TL>(nsites, site, k, 1);
+      U[o] = (TL)m[2 * k];
+      U[o + 1] = (TL)m[2 * k + 1];
+    }
+  }
+  // block sum of the checksum (wraps mod 2^32 by construction)
+  for (int o = 16; o > 0; o >>= 1) cs += __shfl_xor_sync(0xffffffffu, cs, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(checksum, cs);
+}
+
+}  // namespace cgptb
+
+extern "C" {
+
+// raw_host: the data part of a NERSC file (nbytes = sites * 4 * rows * 3 * 2 * float_size); fills the four link lattices
+// (any precision) and returns the NERSC checksum of the data
+int cgptb_nersc_munge(const void* raw_host, size_t nbytes, int float_size, int big_endian, int rows, cgptb_lattice* const U[4],
+                      unsigned int* checksum) {
+  CGPTB_API_BEGIN
+  for (int mu = 0; mu < 4; mu++) CGPTB_ASSERT(U[mu] && U[mu]->otype == 9 && U[mu]->Ls == 0 && U[mu]->cb == CGPTB_FULL && same_shape(U[mu], U[0]));
+  CGPTB_ASSERT((float_size == 4 || float_size == 8) && (rows == 2 || rows == 3));
+  if (g_comm.active) CGPTB_ERR("nersc_munge on a split lattice is not implemented (every rank would read its own block)");
+  const size_t n = U[0]->sites;
+  if (nbytes != n * 4 * (size_t)rows * 6 * (size_t)float_size)
+    CGPTB_ERR("nersc_munge: %zu bytes of data do not match %zu sites of %d x 3 matrices of %d-byte floats", nbytes, n, rows, float_size);
+  unsigned char* raw = 0;
+  CUDA_CHECK(cudaMalloc(&raw, nbytes + 4));
+  unsigned int* dcs = reinterpret_cast<unsigned int*>(reduce_scratch(8));
+  CUDA_CHECK(cudaMemsetAsync(dcs, 0, sizeof(unsigned int), g_stream));
+  CUDA_CHECK(cudaMemcpyAsync(raw, raw_host, nbytes, cudaMemcpyHostToDevice, g_stream));
+  Geom g = make_geom(U[0]->dims4);
+  const unsigned blocks = (unsigned)((n * 4 + 127) / 128);
+  const bool ld = U[0]->prec == CGPTB_DOUBLE;
+#define MUNGE(TF, TL)                                                                                                        \
+  k_nersc_munge<TF, TL><<<blocks, 128, 0, g_stream>>>(g, n, big_endian, rows, raw, (TL*)U[0]->data, (TL*)U[1]->data, (TL*)U[2]->data, \
+                                                      (TL*)U[3]->data, dcs)
+  if (float_size == 4 && ld) MUNGE(float, double);
+  else if (float_size == 4) MUNGE(float, float);
+  else if (ld) MUNGE(double, double);
+  else MUNGE(double, float);
+#undef MUNGE
+  LAUNCH_CHECK();
+  CUDA_CHECK(cudaMemcpyAsync(checksum, dcs, sizeof(unsigned int), cudaMemcpyDeviceToHost, g_stream));
+  CUDA_CHECK(cudaStreamSynchronize(g_stream));
+  CUDA_CHECK(cudaFree(raw));
+  CGPTB_API_END
+}
+}

@@ -185,6 +185,13 @@ int cgptb_random_su3_links(cgptb_random* r, uint64_t grid_key, cgptb_lattice* co
    out[0] = <Re tr P_{mu nu}> / Nc over the six planes, out[1] = <Re tr U_mu> / Nc over the four directions */
 int cgptb_gauge_plaquette(const cgptb_lattice* const U[4], double out[2]);
 
+/* NERSC gauge configurations (lib/gpt/core/io/nersc_io.py:146-199): the data part of the file -> four link lattices on
+   the device: byte order (cgpt.munge_byte_order), third-row reconstruction for 4D_SU3_GAUGE (cgpt.munge_reconstruct_third_row,
+   lib/cgpt/lib/munge.h:21-39), [site][mu] -> [mu][site] (cgpt.munge_inner_outer), checksum (cgpt.util_nersc_checksum,
+   lib/cgpt/lib/checksums/nersc.h:19-33) in one kernel.  rows = 2 (4D_SU3_GAUGE) or 3 (4D_SU3_GAUGE_3x3)        */
+int cgptb_nersc_munge(const void* raw_host, size_t nbytes, int float_size, int big_endian, int rows, cgptb_lattice* const U[4],
+                      unsigned int* checksum);
+
 /* ---- fused fast paths (same results as the opcode sequences they replace) ---------------------------- */
 /* Mpc / Mpc^dag of schur_complement_two (lib/gpt/algorithms/preconditioner/schur_complement_two.py:87-112):
    o = i - Meooe MooeeInv Meooe MooeeInv i ; tmp = 2 work fields of the same shape                       */

@@ -97,3 +97,21 @@ def test_processor_grid_helpers():
     coords = [parallel.processor_coor(r, [1, 1, 2, 4]) for r in range(8)]
     assert coords[0] == [0, 0, 0, 0] and coords[1] == [0, 0, 1, 0] and coords[2] == [0, 0, 0, 1] and coords[7] == [0, 0, 1, 3]
     assert len({tuple(c) for c in coords}) == 8
+
+
+def test_nersc_header_parsing(tmp_path):
+    """host side of g.load: header keys, data offset, non-NERSC files are rejected (no device involved)"""
+    from gpt_b200.io import nersc
+
+    p = tmp_path / "cfg"
+    body = b"\x00" * 64
+    p.write_bytes(b"BEGIN_HEADER\nDATATYPE = 4D_SU3_GAUGE\nDIMENSION_1 = 4\nCHECKSUM =   1a2b\nFLOATING_POINT = IEEE32BIG\nEND_HEADER\n" + body)
+    md, off = nersc.read_header(str(p))
+    assert md["DATATYPE"] == "4D_SU3_GAUGE" and md["CHECKSUM"] == "1a2b" and md["FLOATING_POINT"] == "IEEE32BIG"
+    assert p.read_bytes()[off:] == body
+    q = tmp_path / "other"
+    q.write_bytes(b"\xff\xfe not a header")
+    assert nersc.read_header(str(q)) is None
+    assert nersc.read_header(str(tmp_path / "missing")) is None
+    assert nersc._tolerance("0.588123", 1e-16) == 1e-4 and nersc._tolerance("1.5e-3", 1e-7) == 10.0
+    assert nersc.format.nersc(label="x").params == {"label": "x", "id": "gpt", "sequence_number": 1}

@@ -4,6 +4,8 @@ same seeded inputs, and against the reference's golden fingerprints
 (/root/reference/tests/qcd/fermion_operators.py:371-459).  Tolerances: 1e-12 relative (double), 1e-5 (single)
 as BASELINE.json's north_star states; fingerprints to 100*eps like the reference (fermion_operators.py:527).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -515,3 +517,50 @@ def test_product_rng_lattices(g, precision):
         m = g.qcd.fermion.mobius(U, dict(MOBIUS))
         X = g.inner_product(dst5, g(m * src5))
         assert abs(X - (-8693.09425573421 - 4130.7793316734915j)) / abs(X) < 1e-13
+
+
+# ---------------------------------------------------------------------------------------------------------
+# NERSC gauge configurations (g.load / g.save, device munge kernel); reference test: tests/io/io.py:198-206
+# ---------------------------------------------------------------------------------------------------------
+def test_nersc_roundtrip_and_formats(g, tmp_path):
+    from tests.nersc_util import write_nersc
+
+    dims = [8, 4, 4, 6]
+    rng = oracle_random("nersc")
+    Uo = qcd.gauge_random(rng, dims, scale=0.7)
+    grid = g.grid(dims, g.double)
+    U = to_links(g, grid, Uo)
+    # the reference's own round trip: g.save -> g.load, eps < 1e-14
+    fn = str(tmp_path / "ckpoint.0000")
+    g.save(fn, U, g.format.nersc(label="test"))
+    Up = g.load(fn)
+    assert len(Up) == 4 and Up[0].metadata["DATATYPE"] == "4D_SU3_GAUGE_3x3"
+    for up, u in zip(Up, U):
+        assert (g.norm2(g(up - u)) / g.norm2(u)) ** 0.5 < 1e-14
+    # files written independently of the product: every float format, both data types
+    for fp, dt, tol in [("IEEE64BIG", "4D_SU3_GAUGE_3x3", 1e-15), ("IEEE64LITTLE", "4D_SU3_GAUGE", 1e-13), ("IEEE32BIG", "4D_SU3_GAUGE", 1e-6),
+                        ("IEEE32", "4D_SU3_GAUGE_3x3", 1e-6), ("IEEE64BIG", "4D_SU3_GAUGE", 1e-13)]:
+        fn = str(tmp_path / f"cfg_{fp}_{dt}")
+        write_nersc(fn, Uo, fp, dt)
+        Ul = g.load(fn)
+        assert Ul[0].grid.precision is (g.double if "64" in fp else g.single)
+        for ul, uo in zip(Ul, Uo):
+            assert rel(ul[:], sites(uo, 2)) < tol, (fp, dt)
+        assert abs(g.qcd.gauge.plaquette(Ul) - qcd.plaquette(Uo)) < max(tol, 1e-14) * 10
+    # corrupted data, wrong checksum, wrong plaquette are refused
+    fn = str(tmp_path / "bad_cs")
+    write_nersc(fn, Uo, checksum=0x1234)
+    with pytest.raises(RuntimeError, match="checksum"):
+        g.load(fn)
+    fn = str(tmp_path / "bad_plaq")
+    write_nersc(fn, Uo, plaquette=0.5)
+    with pytest.raises(RuntimeError, match="plaquette"):
+        g.load(fn)
+    fn = str(tmp_path / "truncated")
+    write_nersc(fn, Uo)
+    with open(fn, "r+b") as f:
+        f.truncate(os.path.getsize(fn) - 8)
+    with pytest.raises(RuntimeError, match="bytes of data"):
+        g.load(fn)
+    with pytest.raises(NotImplementedError):
+        g.load(str(tmp_path / "does_not_exist"))
