@@ -107,7 +107,7 @@ def save(filename, U, fmt=None):
     # [site][mu][3][3] in native order for the checksum, big endian on disk
     data = np.stack([np.asarray(u[:]).reshape(-1, 3, 3) for u in U], axis=1).astype(np.complex128)
     cs = int(np.frombuffer(data.tobytes(), dtype="<u4").sum(dtype=np.uint64) & 0xFFFFFFFF)
-    now = datetime.datetime.utcnow().strftime("%c %Z")
+    now = datetime.datetime.now(datetime.timezone.utc).strftime("%c %Z")
     header = f"""BEGIN_HEADER
 HDR_VERSION = 1.0
 DATATYPE = 4D_SU3_GAUGE_3x3

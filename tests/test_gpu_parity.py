@@ -553,7 +553,7 @@ def test_nersc_roundtrip_and_formats(g, tmp_path):
     with pytest.raises(RuntimeError, match="checksum"):
         g.load(fn)
     fn = str(tmp_path / "bad_plaq")
-    write_nersc(fn, Uo, plaquette=0.5)
+    write_nersc(fn, Uo, plaquette=0.512345678)  # nine digits: tolerance 1e-7 (a header value "0.5" would accept anything)
     with pytest.raises(RuntimeError, match="plaquette"):
         g.load(fn)
     fn = str(tmp_path / "truncated")
