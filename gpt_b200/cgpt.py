@@ -33,6 +33,7 @@ class fermion_params(ctypes.Structure):
         ("mass_plus", c_double), ("mass_minus", c_double), ("M5", c_double), ("b", c_double), ("c", c_double),
         ("Ls", c_int),
         ("boundary_phases", c_double * 8),
+        ("mu", c_double),
     ]
 
 
@@ -338,7 +339,7 @@ def lattice_slice_inner_product(b, a, nt):
 # ---- fermion operators -----------------------------------------------------------------------------------
 def _params(p):
     fp = fermion_params()
-    for k in ["mass", "csw_r", "csw_t", "cF", "xi_0", "nu", "mass_plus", "mass_minus", "M5", "b", "c"]:
+    for k in ["mass", "csw_r", "csw_t", "cF", "xi_0", "nu", "mass_plus", "mass_minus", "M5", "b", "c", "mu"]:
         v = p.get(k, None)
         setattr(fp, k, float(v) if v is not None else 0.0)
     fp.isAnisotropic = 1 if p.get("isAnisotropic", False) else 0
@@ -351,7 +352,8 @@ def _params(p):
     return fp
 
 
-_optypes = {"wilson_clover": WILSON_CLOVER, "mobius": MOBIUS}
+# wilson_twisted_mass is the Wilson operator with the parameter mu set (no clover term)
+_optypes = {"wilson_clover": WILSON_CLOVER, "wilson_twisted_mass": WILSON_CLOVER, "mobius": MOBIUS}
 _precisions = {"single": SINGLE, "double": DOUBLE}
 
 

@@ -780,6 +780,36 @@ static void clover_apply(cgptb_fermion_operator* op, bool inverse, bool acc, con
 }
 
 // Mooee / MooeeInv (+Dag) on a half or full field
+// out (+)= (a + i b gamma_5) in, gamma_5 = diag(1, 1, -1, -1): the site-diagonal term of the twisted-mass operator and its
+// inverse (Grid's axpibg5x; lib/cgpt/lib/operators/wilson_twisted_mass.h)
+template <typename T, bool ACC>
+__global__ void __launch_bounds__(128) k_twist(size_t n, const T* __restrict__ in, size_t in_stride, T* __restrict__ out,
+                                               size_t out_stride, T a, T b) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  T psi[24], r[24];
+  load_spinor(in, in_stride, i, psi);
+  if (ACC) load_spinor_rw(out, out_stride, i, r);
+#pragma unroll
+  for (int c = 0; c < 12; c++) {
+    const T bb = c < 6 ? b : -b;
+    const T re = a * psi[2 * c] - bb * psi[2 * c + 1], im = a * psi[2 * c + 1] + bb * psi[2 * c];
+    r[2 * c] = ACC ? r[2 * c] + re : re;
+    r[2 * c + 1] = ACC ? r[2 * c + 1] + im : im;
+  }
+  store_spinor(out, out_stride, i, r);
+}
+
+template <typename T>
+static void twist_apply(const cgptb_lattice* in, cgptb_lattice* out, bool acc, double a, double b) {
+  unsigned blocks = (unsigned)((in->sites + 127) / 128);
+  if (acc)
+    k_twist<T, true><<<blocks, 128, 0, g_stream>>>(in->sites, (const T*)in->data, in->sites, (T*)out->data, out->sites, (T)a, (T)b);
+  else
+    k_twist<T, false><<<blocks, 128, 0, g_stream>>>(in->sites, (const T*)in->data, in->sites, (T*)out->data, out->sites, (T)a, (T)b);
+  LAUNCH_CHECK();
+}
+
 void op_mooee(cgptb_fermion_operator* op, bool inverse, bool dag, bool acc, const cgptb_lattice* in, cgptb_lattice* out) {
   if (op->type == CGPTB_MOBIUS) {
     if (inverse) {
@@ -794,8 +824,26 @@ void op_mooee(cgptb_fermion_operator* op, bool inverse, bool dag, bool acc, cons
     clover_apply(op, inverse, acc, in, out);  // Hermitian: dag == non-dag
     return;
   }
-  // plain Wilson: (m0 + 1 + 3 nu/xi_0) psi   (lib/cgpt/lib/operators/implementation.h:21-29)
   double diag = op->p.mass + 1.0 + 3.0 * op->p.nu / op->p.xi_0;
+  if (op->p.mu != 0.0) {
+    // twisted mass: (diag + i mu gamma_5), inverse (diag - i mu gamma_5) / (diag^2 + mu^2), dagger: mu -> -mu
+    op->check_field(in);
+    op->check_field(out);
+    CGPTB_ASSERT(in->data != out->data || !acc);
+    if (!acc) out->cb = in->cb;
+    double a = diag, b = dag ? -op->p.mu : op->p.mu;
+    if (inverse) {
+      const double den = diag * diag + op->p.mu * op->p.mu;
+      a = diag / den;
+      b = -b / den;
+    }
+    if (op->prec == CGPTB_SINGLE)
+      twist_apply<float>(in, out, acc, a, b);
+    else
+      twist_apply<double>(in, out, acc, a, b);
+    return;
+  }
+  // plain Wilson: (m0 + 1 + 3 nu/xi_0) psi   (lib/cgpt/lib/operators/implementation.h:21-29)
   double coef[2] = {inverse ? 1.0 / diag : diag, 0.0};
   const cgptb_lattice* a[1] = {in};
   op->check_field(in);
@@ -965,6 +1013,7 @@ int cgptb_create_fermion_operator(cgptb_fermion_operator** out, int optype, int 
       if (params->boundary_phases[6] == 0.0 && params->boundary_phases[7] == 0.0)
         CGPTB_ERR("open boundary conditions (boundary_phases[3] == 0) are not implemented");
       if (params->xi_0 == 0.0) CGPTB_ERR("xi_0 must be non-zero");
+      if (params->mu != 0.0 && (params->csw_r != 0.0 || params->csw_t != 0.0)) CGPTB_ERR("twisted mass with a clover term is not a GPT operator");
     }
     op->import_gauge(U);
   } catch (...) {

@@ -22,3 +22,12 @@ def wilson_clover(U, params):
         raise NotImplementedError("open boundary conditions are a SURVEY 8(f2) next row")
     assert params["cF"] == 1.0  # forbid usage of cF without open bc
     return fine_operator("wilson_clover", U, params, otype=g.ot_vector_spin_color(4, 3))
+
+
+@g.params_convention(mass=None, mu=None, boundary_phases=None)
+def wilson_twisted_mass(U, params):
+    """g.qcd.fermion.wilson_twisted_mass (lib/gpt/qcd/fermion/wilson.py:99-107): Wilson hopping term with the site-diagonal
+    term (4 + mass) + i mu gamma_5; isotropic, no clover term"""
+    params = copy.deepcopy(params)
+    params.update(csw_r=0.0, csw_t=0.0, cF=1.0, xi_0=1.0, nu=1.0, isAnisotropic=False)
+    return fine_operator("wilson_twisted_mass", U, params, otype=g.ot_vector_spin_color(4, 3))

@@ -141,6 +141,8 @@ typedef struct {
   int Ls;
   /* both: 4 complex boundary phases (re,im) */
   double boundary_phases[8];
+  /* wilson_twisted_mass (lib/cgpt/lib/operators/wilson_twisted_mass.h): Mooee = (4 + mass) + i mu gamma_5; 0 = untwisted */
+  double mu;
 } cgptb_fermion_params;
 
 /* cgpt.create_fermion_operator(optype, prec, params): U = 4 colour-matrix lattices on the full 4d grid */

@@ -234,7 +234,7 @@ class wilson_clover:
     """
 
     def __init__(self, U, kappa=None, mass=None, csw_r=0.0, csw_t=0.0, xi_0=1.0, nu=1.0,
-                 isAnisotropic=False, boundary_phases=(1, 1, 1, 1), cF=1.0):
+                 isAnisotropic=False, boundary_phases=(1, 1, 1, 1), cF=1.0, mu=0.0):
         if kappa is not None:
             assert mass is None
             mass = 1.0 / kappa / 2.0 - 4.0
@@ -246,6 +246,10 @@ class wilson_clover:
         self.mass = mass
         self.coef = (nu / xi_0, nu / xi_0, nu / xi_0, 1.0)
         self.diag = mass + 1.0 + 3.0 * nu / xi_0
+        # twisted mass (g.qcd.fermion.wilson_twisted_mass, lib/gpt/qcd/fermion/wilson.py:99-107; Grid's WilsonTMFermion):
+        # Mooee = (4 + m) + i mu gamma_5, gamma_5 = diag(1, 1, -1, -1) in GPT's basis (lib/gpt/core/gamma.py:28-41)
+        self.mu = mu
+        assert mu == 0.0 or (csw_r == 0.0 and csw_t == 0.0)
         self.clover = None
         if csw_r != 0.0 or csw_t != 0.0:
             cl = np.zeros(U[0].shape[:4] + (4, 4, 3, 3), dtype=np.complex128)
@@ -271,12 +275,21 @@ class wilson_clover:
         sh = psi.shape
         return np.einsum("...ab,...b->...a", mat, psi.reshape(sh[:4] + (12,))).reshape(sh)
 
+    def _twist(self, psi, a, b):
+        g5 = np.array([1.0, 1.0, -1.0, -1.0]).reshape((1,) * (psi.ndim - 2) + (4, 1))
+        return (psi.dtype.type(a) * psi + psi.dtype.type(1j * b) * (g5 * psi)).astype(psi.dtype)
+
     def Mooee(self, psi, dag=False):  # on a full-lattice field (== Mdiag)
+        if self.mu != 0.0:
+            return self._twist(psi, self.diag, -self.mu if dag else self.mu)
         if self.clover is None:
             return psi.dtype.type(self.diag) * psi
         return self._site(adj(self.clover) if dag else self.clover, psi)
 
     def MooeeInv(self, psi, dag=False):
+        if self.mu != 0.0:
+            den = self.diag**2 + self.mu**2
+            return self._twist(psi, self.diag / den, (self.mu if dag else -self.mu) / den)
         if self.clover is None:
             return psi.dtype.type(1.0 / self.diag) * psi
         return self._site(adj(self.clover_inv) if dag else self.clover_inv, psi)

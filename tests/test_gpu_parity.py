@@ -139,16 +139,20 @@ def _ops4(g, fields, params, precision):
     p = prec_of(g, precision)
     grid = g.grid(DIMS, p)
     U = to_links(g, grid, fields["U"])
-    w = g.qcd.fermion.wilson_clover(U, dict(params))
+    ctor = g.qcd.fermion.wilson_twisted_mass if "mu" in params else g.qcd.fermion.wilson_clover
+    w = ctor(U, dict(params))
     Uo = [u.astype(p.complex_dtype) for u in fields["U"]]
     wo = qcd.wilson_clover(Uo, **params)
     return grid, w, wo
 
 
+TWISTED = dict(mass=-1.8, mu=0.2, boundary_phases=[1.0, 1.0, 1.0, -1.0])  # tests/qcd/fermion_operators.py:365-369
+
+
 @pytest.mark.parametrize("precision", ["double", "single"])
-@pytest.mark.parametrize("name", ["wilson", "clover"])
+@pytest.mark.parametrize("name", ["wilson", "clover", "twisted"])
 def test_wilson_clover_full(g, fields, name, precision):
-    params = WILSON if name == "wilson" else CLOVER
+    params = {"wilson": WILSON, "clover": CLOVER, "twisted": TWISTED}[name]
     grid, w, wo = _ops4(g, fields, params, precision)
     tol = TOL[precision]
     src_np = fields["srcw"].astype(grid.precision.complex_dtype)
@@ -163,7 +167,8 @@ def test_wilson_clover_full(g, fields, name, precision):
     if precision == "double":
         dst = to_spinor(g, grid, fields["dstw"])
         golden = {"wilson": (-999.7564252326631 - 466.7758727463097j, -961.5053827614738 - 3468.430447866095j),
-                  "clover": (-946.8714968698364 - 427.1253034080037j, -908.620454398646 - 3428.779878527792j)}[name]
+                  "clover": (-946.8714968698364 - 427.1253034080037j, -908.620454398646 - 3428.779878527792j),
+                  "twisted": (-5.665095757463064 + 373.96051873176737j, -440.5312395819657 - 1102.362512575698j)}[name]
         X = g.inner_product(dst, g(w * src))
         assert abs(X - golden[0]) / abs(golden[0]) < 1e-13
         X = g.inner_product(dst, g(w.Mdiag * src))
@@ -171,9 +176,9 @@ def test_wilson_clover_full(g, fields, name, precision):
 
 
 @pytest.mark.parametrize("precision", ["double", "single"])
-@pytest.mark.parametrize("name", ["wilson", "clover"])
+@pytest.mark.parametrize("name", ["wilson", "clover", "twisted"])
 def test_wilson_clover_eo(g, fields, name, precision):
-    params = WILSON if name == "wilson" else CLOVER
+    params = {"wilson": WILSON, "clover": CLOVER, "twisted": TWISTED}[name]
     grid, w, wo = _ops4(g, fields, params, precision)
     tol = TOL[precision]
     e = qcd.eo_ops(wo)

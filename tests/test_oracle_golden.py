@@ -92,6 +92,21 @@ def test_wilson_fingerprints(fingerprint_fields):
     assert _close(qcd.inner_product(f["dstw"], w.Mdiag(f["srcw"])), -908.620454398646 - 3428.779878527792j)
 
 
+def test_wilson_twisted_mass_fingerprints(fingerprint_fields):
+    # tests/qcd/fermion_operators.py:365-369,387-390
+    f = fingerprint_fields
+    w = qcd.wilson_clover(f["Uw"], mass=-1.8, mu=0.2, boundary_phases=[1.0, 1.0, 1.0, -1.0])
+    assert _close(qcd.inner_product(f["dstw"], w.M(f["srcw"])), -5.665095757463064 + 373.96051873176737j)
+    assert _close(qcd.inner_product(f["dstw"], w.Mdiag(f["srcw"])), -440.5312395819657 - 1102.362512575698j)
+    # MooeeInv Mooee = 1, Mdag = adjoint of M
+    x = w.MooeeInv(w.Mooee(f["srcw"]))
+    assert np.linalg.norm(x - f["srcw"]) / np.linalg.norm(f["srcw"]) < 1e-14
+    x = w.MooeeInv(w.Mooee(f["srcw"], dag=True), dag=True)
+    assert np.linalg.norm(x - f["srcw"]) / np.linalg.norm(f["srcw"]) < 1e-14
+    a, b = qcd.inner_product(f["dstw"], w.M(f["srcw"])), qcd.inner_product(w.Mdag(f["dstw"]), f["srcw"])
+    assert abs(a - b) / abs(a) < 1e-13
+
+
 def test_mobius_fingerprints(fingerprint_fields):
     f = fingerprint_fields
     m = qcd.mobius(f["U"], **MOBIUS)
