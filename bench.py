@@ -138,7 +138,7 @@ def run_native(args):
 
     from gpt_b200 import parallel
 
-    mpi = parallel.default_mpi(world)  # T first, then Z
+    mpi = [1, 1, 1, world]  # BASELINE.json configs[2]: "1 GPU then T-split across 2/4/8 B200" (weak scaling in T)
     if world > 1:
         parallel.setup(dist, mpi)
     dims = list(DIMS)  # local extents; weak scaling: the global lattice grows with the processor grid

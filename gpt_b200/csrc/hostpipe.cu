@@ -168,7 +168,7 @@ int cgptb_apply_fermion_operator_host(cgptb_fermion_operator* op, int opcode, co
   cgptb_lattice* fout = pipe_field(g_pipe.f_out, op);
   if (nbytes != fin->bytes()) CGPTB_ERR("apply_fermion_operator_host: buffers have %zu bytes, the field needs %zu", nbytes, fin->bytes());
   const char* e = getenv("CGPTB_HOSTPIPE_SLABS");
-  int nslab = e ? atoi(e) : 16;
+  int nslab = e ? atoi(e) : 32;  // measured at 32^3x64x12: 8 slabs 63.3 ms, 16: 56.3, 32: 53.6 per call
   while (nslab > 3 && op->g.L[3] % nslab) nslab--;
   if (pipeline_usable(op, opcode, nslab)) {
     apply_host_pipelined(op, opcode == 4001, (const float*)src_host, (float*)dst_host, nslab);
