@@ -427,6 +427,35 @@ class matrix_operator:
     def specialized_singlet_callable(self):
         return self.mat if not self.accept_list else self
 
+    def packed(self):
+        """operator on a 5d grid whose fifth dimension enumerates right-hand sides -> operator on lists of n_rhs 4d fields
+        (lib/gpt/core/operator/matrix_operator.py:200-239); packing and unpacking are device copies"""
+        vs5 = self.vector_space
+        grid5 = vs5[1].grid
+        assert grid5 is not None and grid5.nd == 5
+        n_rhs = grid5.fdimensions[0]
+
+        def _packed(dst, src, op5):
+            assert len(src) == n_rhs and len(dst) == n_rhs
+            t_src = lattice(grid5, src[0].otype)
+            t_dst = lattice(grid5, dst[0].otype)
+            if grid5.cb.n != 1:
+                t_src.checkerboard(src[0].checkerboard())
+            cgpt.lattice_pack_rhs(t_src.obj, [x.obj for x in src])
+            op5(t_dst, t_src)
+            cgpt.lattice_pack_rhs(t_dst.obj, [x.obj for x in dst], unpack=True)
+
+        def wrap(get):
+            return lambda dst, src: _packed(dst, src, get())
+
+        grid4 = grid5.removed_dimension(0)
+        vs4 = tuple(vector_space(grid4, v.otype, v.cb) if v is not None else None for v in vs5)
+        return matrix_operator(
+            mat=wrap(lambda: self), adj_mat=wrap(lambda: self.adj()),
+            inv_mat=wrap(lambda: self.inv()) if self.inv_mat is not None else None,
+            adj_inv_mat=wrap(lambda: self.adj().inv()) if self.adj_inv_mat is not None else None,
+            vector_space=vs4, accept_guess=self.accept_guess, accept_list=True)
+
     def __mul__(self, other):
         if isinstance(other, matrix_operator):
             return matrix_operator_product([self, other])

@@ -155,6 +155,29 @@ static void new_lattice(cgptb_lattice** out, const int dims4[4], int Ls, int pre
 
 using namespace cgptb;
 
+namespace cgptb {
+// gpt.pack of n 4d fields into one 5d field with the list index as the fifth dimension and back
+// (matrix_operator.packed(), lib/gpt/core/operator/matrix_operator.py:200-239): 5d site = 4d site * n + s in both halves
+template <bool PACK>
+__global__ void k_pack_rhs(size_t n4, int n, int s, int nblk, size_t blk16, const uint4* __restrict__ a4, uint4* __restrict__ a5,
+                           const uint4* __restrict__ a5c, uint4* __restrict__ a4w) {
+  // one thread per (component block, 4d site, 16 bytes of the block)
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)nblk * n4 * blk16) return;
+  const size_t q = idx % blk16;
+  const size_t r = idx / blk16;
+  const size_t i = r % n4;
+  const size_t k = r / n4;
+  const size_t o4 = (k * n4 + i) * blk16 + q;
+  const size_t o5 = (k * n4 * n + i * n + s) * blk16 + q;
+  if (PACK)
+    a5[o5] = a4[o4];
+  else
+    a4w[o4] = a5c[o5];
+}
+
+}  // namespace cgptb
+
 extern "C" {
 
 int cgptb_init(int device) {
@@ -300,6 +323,33 @@ int cgptb_lattice_export_device(const cgptb_lattice* l, void* dev, size_t nbytes
   CGPTB_API_BEGIN
   if (nbytes != l->bytes()) CGPTB_ERR("export: buffer has %zu bytes, lattice needs %zu", nbytes, l->bytes());
   layout_device<false>(const_cast<cgptb_lattice*>(l), dev);
+  CGPTB_API_END
+}
+
+int cgptb_lattice_pack_rhs(cgptb_lattice* l5, cgptb_lattice* const* l4, int n, int unpack) {
+  CGPTB_API_BEGIN
+  CGPTB_ASSERT(l5 && l4 && n > 0 && l5->Ls == n);
+  for (int s = 0; s < n; s++) {
+    const cgptb_lattice* a = l4[s];
+    CGPTB_ASSERT(a && a->Ls == 0 && a->prec == l5->prec && a->otype == l5->otype && a->sites * n == l5->sites);
+    for (int i = 0; i < 4; i++) CGPTB_ASSERT(a->dims4[i] == l5->dims4[i]);
+    if (unpack) {
+      l4[s]->cb = l5->cb;
+    } else {
+      if (s == 0) l5->cb = a->cb;
+      CGPTB_ASSERT(a->cb == l5->cb);
+    }
+    const size_t blk16 = a->block_bytes() / 16;
+    CGPTB_ASSERT(a->block_bytes() % 16 == 0);
+    const int nblk = a->otype / a->cpb();
+    const size_t nthr = (size_t)nblk * a->sites * blk16;
+    const unsigned blocks = (unsigned)((nthr + 255) / 256);
+    if (unpack)
+      k_pack_rhs<false><<<blocks, 256, 0, g_stream>>>(a->sites, n, s, nblk, blk16, 0, 0, (const uint4*)l5->data, (uint4*)l4[s]->data);
+    else
+      k_pack_rhs<true><<<blocks, 256, 0, g_stream>>>(a->sites, n, s, nblk, blk16, (const uint4*)a->data, (uint4*)l5->data, 0, 0);
+    LAUNCH_CHECK();
+  }
   CGPTB_API_END
 }
 

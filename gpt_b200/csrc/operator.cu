@@ -289,13 +289,15 @@ __global__ void k_export5(size_t n4, int ls, const T* __restrict__ in5, T* __res
 // (lib/gpt/qcd/fermion/reference/wilson_clover.py:92-139,202-220)
 // ----------------------------------------------------------------------------------------------------
 template <typename T, bool ACC>
-__global__ void __launch_bounds__(128) k_clover_apply(size_t n, const T* __restrict__ in, size_t in_stride, T* __restrict__ out,
+__global__ void __launch_bounds__(128) k_clover_apply(size_t n, int ls, const T* __restrict__ in, size_t in_stride, T* __restrict__ out,
                                                       size_t out_stride, const T* __restrict__ clov) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  // n: 4d sites of this parity; ls > 1: multi-rhs field, the ls right-hand sides of a site share its clover blocks
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n * ls) return;
+  const size_t i = j / ls;
   T psi[24], r[24];
-  load_spinor(in, in_stride, i, psi);
-  if (ACC) load_spinor_rw(out, out_stride, i, r);
+  load_spinor(in, in_stride, j, psi);
+  if (ACC) load_spinor_rw(out, out_stride, j, r);
 #pragma unroll
   for (int blk = 0; blk < 2; blk++) {
     T o[12];
@@ -326,7 +328,7 @@ __global__ void __launch_bounds__(128) k_clover_apply(size_t n, const T* __restr
 #pragma unroll
     for (int k = 0; k < 12; k++) r[blk * 12 + k] = ACC ? r[blk * 12 + k] + o[k] : o[k];
   }
-  store_spinor(out, out_stride, i, r);
+  store_spinor(out, out_stride, j, r);
 }
 
 struct M3 {
@@ -754,26 +756,27 @@ static void clover_apply(cgptb_fermion_operator* op, bool inverse, bool acc, con
   CGPTB_ASSERT(in->sites == out->sites);
   if (!acc) out->cb = in->cb;
   size_t half = op->g.half4;
+  const int ls = op->ls();
   int threads = 128;
-  unsigned blocks = (unsigned)((half + threads - 1) / threads);
+  unsigned blocks = (unsigned)((half * ls + threads - 1) / threads);
   for (int p = 0; p < 2; p++) {
     if (in->cb != CGPTB_FULL && in->cb != p) continue;
-    size_t off = in->cb == CGPTB_FULL ? (size_t)p * half : 0;
+    size_t off = in->cb == CGPTB_FULL ? (size_t)p * half * ls : 0;
     void* cl = inverse ? op->clov_inv[p] : op->clov[p];
     if (op->prec == CGPTB_SINGLE) {
       const float* pin = (const float*)in->data + off * 8;
       float* pout = (float*)out->data + off * 8;
       if (acc)
-        k_clover_apply<float, true><<<blocks, threads, 0, g_stream>>>(half, pin, in->sites, pout, out->sites, (const float*)cl);
+        k_clover_apply<float, true><<<blocks, threads, 0, g_stream>>>(half, ls, pin, in->sites, pout, out->sites, (const float*)cl);
       else
-        k_clover_apply<float, false><<<blocks, threads, 0, g_stream>>>(half, pin, in->sites, pout, out->sites, (const float*)cl);
+        k_clover_apply<float, false><<<blocks, threads, 0, g_stream>>>(half, ls, pin, in->sites, pout, out->sites, (const float*)cl);
     } else {
       const double* pin = (const double*)in->data + off * 4;
       double* pout = (double*)out->data + off * 4;
       if (acc)
-        k_clover_apply<double, true><<<blocks, threads, 0, g_stream>>>(half, pin, in->sites, pout, out->sites, (const double*)cl);
+        k_clover_apply<double, true><<<blocks, threads, 0, g_stream>>>(half, ls, pin, in->sites, pout, out->sites, (const double*)cl);
       else
-        k_clover_apply<double, false><<<blocks, threads, 0, g_stream>>>(half, pin, in->sites, pout, out->sites, (const double*)cl);
+        k_clover_apply<double, false><<<blocks, threads, 0, g_stream>>>(half, ls, pin, in->sites, pout, out->sites, (const double*)cl);
     }
     LAUNCH_CHECK();
   }
@@ -1004,7 +1007,9 @@ int cgptb_create_fermion_operator(cgptb_fermion_operator** out, int optype, int 
   for (int i = 0; i < 4; i++) op->dims4[i] = U[0]->dims4[i];
   op->g = make_geom(op->dims4);
   op->p = *params;
-  op->Ls = optype == CGPTB_MOBIUS ? params->Ls : 0;
+  // Wilson-clover with Ls > 0: multi-rhs operator, the fifth dimension enumerates right-hand sides that share the links
+  // (wilson_clover(n_rhs=...), lib/gpt/qcd/fermion/wilson.py:134-138)
+  op->Ls = params->Ls > 0 ? params->Ls : 0;
   try {
     if (optype == CGPTB_MOBIUS) {
       if (params->Ls < 1) CGPTB_ERR("mobius needs Ls >= 1");

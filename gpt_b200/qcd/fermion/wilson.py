@@ -16,8 +16,12 @@ def wilson_clover(U, params):
         params["mass"] = 1.0 / params["kappa"] / 2.0 - 4.0
         del params["kappa"]
     if params["n_rhs"] > 1:
-        raise NotImplementedError("multi-rhs Wilson-clover (n_rhs > 1) is a SURVEY 8(f1) next row")
-    params["multi_rhs"] = False
+        # multi-rhs operator: the right-hand sides are the fifth dimension of the fermion grid and share every link
+        # (and clover block) load; use .packed() to apply it to a list of 4d fields (wilson.py:134-138)
+        params["multi_rhs"] = True
+        params["Ls"] = params["n_rhs"]
+    else:
+        params["multi_rhs"] = False
     if params["boundary_phases"][-1] == 0.0:
         raise NotImplementedError("open boundary conditions are a SURVEY 8(f2) next row")
     assert params["cF"] == 1.0  # forbid usage of cF without open bc

@@ -80,6 +80,9 @@ int cgptb_create_lattice(cgptb_lattice** out, const int dims4[4], int Ls, int pr
 int cgptb_create_lattice_view(cgptb_lattice** out, const int dims4[4], int Ls, int precision, int otype, int cb,
                               void* device_ptr);
 int cgptb_delete_lattice(cgptb_lattice* l);
+/* gpt.pack of n 4d fields <-> one 5d field whose fifth dimension is the list index (matrix_operator.packed(),
+   lib/gpt/core/operator/matrix_operator.py:200-239); unpack != 0: 5d -> the n 4d fields */
+int cgptb_lattice_pack_rhs(cgptb_lattice* l5, cgptb_lattice* const* l4, int n, int unpack);
 size_t cgptb_lattice_bytes(const cgptb_lattice* l);
 size_t cgptb_lattice_sites(const cgptb_lattice* l);
 void* cgptb_lattice_device_ptr(cgptb_lattice* l);

@@ -569,3 +569,38 @@ def test_nersc_roundtrip_and_formats(g, tmp_path):
         g.load(fn)
     with pytest.raises(NotImplementedError):
         g.load(str(tmp_path / "does_not_exist"))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# multi-rhs Wilson-clover: wilson_clover(n_rhs=...).packed() (tests/qcd/fermion_operators.py:97-132)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision,n_rhs", [("double", 4), ("single", 12), ("single", 3)])
+def test_wilson_multi_rhs_packed(g, fields, precision, n_rhs):
+    """the n_rhs columns go through the stencil as the fifth dimension of one field (in single precision with n_rhs = 12 this is
+    the TMA sweep kernel) and must give what the single-rhs operator gives column by column"""
+    params = dict(mass=0.123, csw_r=0.6, csw_t=0.6, cF=1.0, xi_0=1.0, nu=1.0, isAnisotropic=False, boundary_phases=[1, 1, 1, -1])
+    p = prec_of(g, precision)
+    grid = g.grid(DIMS, p)
+    U = to_links(g, grid, fields["U"])
+    single = g.qcd.fermion.wilson_clover(U, dict(params))
+    multi5 = g.qcd.fermion.wilson_clover(U, dict(params, n_rhs=n_rhs))
+    multi = multi5.packed()
+    wo = qcd.wilson_clover([u.astype(p.complex_dtype) for u in fields["U"]], **params)
+    rng = oracle_random("multi rhs")
+    cols = [rng.cnormal(DIMS, (4, 3)).astype(p.complex_dtype) for _ in range(n_rhs)]
+    test = [to_spinor(g, grid, c) for c in cols]
+    tol = 1e-15 if precision == "double" else 2e-6
+    for op1, opn, ref in [(single, multi, wo.M), (single.adj(), multi.adj(), wo.Mdag), (single.Dhop, multi5.Dhop.packed(), wo.Dhop),
+                          (single.Mdiag, multi5.Mdiag.packed(), wo.Mdiag)]:
+        test0 = [op1(t) for t in test]
+        test1 = opn(test)
+        assert len(test1) == n_rhs
+        for i in range(n_rhs):
+            eps = (g.norm2(g(test0[i] - test1[i])) / g.norm2(test0[i])) ** 0.5
+            assert eps < tol, (i, eps)
+            assert rel(from_spinor(test1[i], cols[i]), ref(cols[i])) < TOL[precision]
+    # even-odd pieces on the 5d grid: MooeeInv Mooee = 1 for every column
+    half = [to_spinor(g, single.F_grid_eo, c, g.odd) for c in cols]
+    back = multi5.Mooee.inv().packed()(multi5.Mooee.packed()(half))
+    for b, h in zip(back, half):
+        assert (g.norm2(g(b - h)) / g.norm2(h)) ** 0.5 < (1e-13 if precision == "double" else 1e-5)
