@@ -10,7 +10,8 @@
 //     the device layout (k_slab_layout) and, as soon as the slabs j-1, j, j+1 are resident, runs the hopping term on the
 //     time slices of slab j only (the TMA sweep kernel takes a time range), reorders the result back into GPT order
 //     and copy engine 2 downloads it while later slabs are still being uploaded;
-//   * the slabs 0 and N-1 need each other (periodic lattice) and are done last.
+//   * the slabs 0 and N-1 need each other (periodic lattice) and are done last; on a lattice split in t across GPUs they
+//     are the only ones that need the neighbours' faces, so the halo exchange happens once, at the end.
 //
 // Everything else (other opcodes, double precision, split lattices, lattices the sweep kernel does not tile) goes through
 // the plain import -> apply -> export sequence, so the call is valid for every opcode of register.h:2-20.
@@ -86,7 +87,9 @@ static cgptb_lattice* pipe_field(cgptb_lattice*& slot, const cgptb_fermion_opera
 static bool pipeline_usable(const cgptb_fermion_operator* op, int opcode, int nslab) {
   if (getenv("CGPTB_NO_HOSTPIPE")) return false;
   if (opcode != 3001 && opcode != 4001) return false;  // Dhop, DhopDag (register.h:13-14)
-  if (!dhop_tma_usable(op) || op->g.comm_mask) return false;
+  // a lattice split in t only keeps every hop of the interior slabs on this rank; the first and the last slab go through
+  // the regular halo exchange at the end
+  if (!dhop_tma_usable(op) || (op->g.comm_mask & ~8)) return false;
   return op->g.L[3] % nslab == 0 && op->g.L[3] / nslab >= 1 && nslab >= 3;
 }
 
@@ -130,18 +133,34 @@ static void apply_host_pipelined(cgptb_fermion_operator* op, bool dag, const flo
     CUDA_CHECK(cudaMemcpyAsync(P.raw_in + (size_t)j * slab_reals, host_src + (size_t)j * slab_reals, slab_bytes, cudaMemcpyHostToDevice, P.h2d));
     CUDA_CHECK(cudaEventRecord(P.ev_in[j], P.h2d));
   }
-  auto compute_slab = [&](int j) {
-    const int t0 = j * nt;
-    for (int p = 0; p < 2; p++) {
-      const float* pin = (const float*)fin->data + (size_t)(1 - p) * half * 8;
-      float* pout = (float*)fout->data + (size_t)p * half * 8;
-      dhop_half_f32_tma(op, dag, pin, stride, pout, stride, p, t0, nt);
-    }
-    k_slab_layout<false><<<blocks, 256, 0, g_stream>>>(g, ls, t0, nt, P.raw_out + (size_t)j * slab_reals, (float*)fout->data, stride);
+  auto export_slab = [&](int j) {
+    k_slab_layout<false><<<blocks, 256, 0, g_stream>>>(g, ls, j * nt, nt, P.raw_out + (size_t)j * slab_reals, (float*)fout->data, stride);
     LAUNCH_CHECK();
     CUDA_CHECK(cudaEventRecord(P.ev_out[j], g_stream));
     CUDA_CHECK(cudaStreamWaitEvent(P.d2h, P.ev_out[j], 0));
     CUDA_CHECK(cudaMemcpyAsync(host_dst + (size_t)j * slab_reals, P.raw_out + (size_t)j * slab_reals, slab_bytes, cudaMemcpyDeviceToHost, P.d2h));
+  };
+  auto compute_slab = [&](int j) {
+    for (int p = 0; p < 2; p++) {
+      const float* pin = (const float*)fin->data + (size_t)(1 - p) * half * 8;
+      float* pout = (float*)fout->data + (size_t)p * half * 8;
+      dhop_half_f32_tma(op, dag, pin, stride, pout, stride, p, j * nt, nt);
+    }
+    export_slab(j);
+  };
+  // the two slabs at the ends of the time direction: periodic neighbours of each other on one GPU; on a lattice split in t
+  // their outermost slices also take the faces of the neighbouring ranks (pack -> NCCL -> interior -> exterior, halo.cu)
+  auto compute_boundary_slabs = [&]() {
+    for (int p = 0; p < 2; p++) {
+      const float* pin = (const float*)fin->data + (size_t)(1 - p) * half * 8;
+      float* pout = (float*)fout->data + (size_t)p * half * 8;
+      if (g.comm_mask) halo_begin(op, dag, p, pin, stride);
+      dhop_half_f32_tma(op, dag, pin, stride, pout, stride, p, (nslab - 1) * nt, nt);
+      dhop_half_f32_tma(op, dag, pin, stride, pout, stride, p, 0, nt);
+      if (g.comm_mask) halo_end(op, dag, p, pout, stride);
+    }
+    export_slab(nslab - 1);
+    export_slab(0);
   };
   for (int j = 0; j < nslab; j++) {
     CUDA_CHECK(cudaStreamWaitEvent(g_stream, P.ev_in[j], 0));
@@ -149,8 +168,7 @@ static void apply_host_pipelined(cgptb_fermion_operator* op, bool dag, const flo
     LAUNCH_CHECK();
     if (j >= 2) compute_slab(j - 1);
   }
-  compute_slab(nslab - 1);
-  compute_slab(0);
+  compute_boundary_slabs();
   CUDA_CHECK(cudaStreamSynchronize(P.d2h));
   CUDA_CHECK(cudaStreamSynchronize(g_stream));
 }
