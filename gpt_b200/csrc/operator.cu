@@ -45,6 +45,9 @@ __global__ void k_build_links(Geom g, int p, size_t nsitesU, const TU* U0, const
     bool last = gc == lc.gL[mu] - 1;
     double fr = lc.w[mu] * (last ? lc.ph[2 * mu] : 1.0);
     double fi = lc.w[mu] * (last ? lc.ph[2 * mu + 1] : 0.0);
+    // open boundary conditions: the operator is P D P with P the projector on 0 < t < T-1, i.e. nothing hops out of the
+    // slices 0 and T-1 either: U_t(t = 0) and U_t(t = T-2) vanish like U_t(t = T-1) (phase 0) does
+    if (lc.open_bc && mu == 3 && (gc == 0 || gc == lc.gL[3] - 2)) fr = fi = 0.0;
     for (int k = 0; k < 9; k++) {
       size_t o = elem_offset<TU>(nsitesU, site, k, 1);
       double ur = ghost ? ghost[(ft * 9 + k) * 2] : (double)U[mu][o];
@@ -117,6 +120,31 @@ static void dhop_half(cgptb_fermion_operator* op, bool dag, const cgptb_lattice*
   if (op->g.comm_mask) halo_end(op, dag, p_out, pout, out->sites);
 }
 
+// results vanish on the global time slices 0 and T-1 (lib/gpt/qcd/fermion/boundary_conditions.py:23-31); in the device layout
+// a time slice of one parity is contiguous in every component plane
+void apply_open_boundaries(const cgptb_fermion_operator* op, cgptb_lattice* l) {
+  if (!op->open_bc) return;
+  const Geom& g = op->g;
+  const int* goff = op->goff;
+  const int* gL = op->gL;
+  const int* dims4 = op->dims4;
+  const size_t rs = l->real_size(), blk = 32 / rs;
+  const size_t slice = (size_t)g.hx * g.L[1] * g.L[2] * op->ls();  // blocks of one parity per time slice
+  const size_t half = slice * g.L[3];
+  const int nplanes = (int)(24 / blk);
+  const int nhalves = l->cb == CGPTB_FULL ? 2 : 1;
+  for (int side = 0; side < 2; side++) {
+    if (side == 0 && goff[3] != 0) continue;
+    if (side == 1 && goff[3] + dims4[3] != gL[3]) continue;
+    const size_t t = side == 0 ? 0 : (size_t)g.L[3] - 1;
+    for (int k = 0; k < nplanes; k++)
+      for (int h = 0; h < nhalves; h++) {
+        char* p = (char*)l->data + ((size_t)k * l->sites + (size_t)h * half + t * slice) * 32;
+        CUDA_CHECK(cudaMemsetAsync(p, 0, slice * 32, g_stream));
+      }
+  }
+}
+
 void op_dhop(cgptb_fermion_operator* op, bool dag, const cgptb_lattice* in, cgptb_lattice* out) {
   op->check_field(in);
   op->check_field(out);
@@ -137,6 +165,7 @@ void op_dhop(cgptb_fermion_operator* op, bool dag, const cgptb_lattice* in, cgpt
     else
       dhop_half<double>(op, dag, in, out, out->cb);
   }
+  apply_open_boundaries(op, out);
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -409,6 +438,8 @@ __device__ inline M3 clover_v(const Geom& g, size_t ns, const TU* Umu, const TU*
 }
 
 struct CloverCoef {
+  int open_bc, T;      // open boundary conditions: clover term -> -csw_t/2 on t = 0, T-1; += cF - 1 on t = 1, T-2
+  double edge, cF1;    // -csw_t / 2, cF - 1     (lib/gpt/qcd/fermion/reference/wilson_clover.py:106-125)
   double diag;
   double c[6];         // -1/2 * c_{mu nu} for planes (0,1),(0,2),(0,3),(1,2),(1,3),(2,3)
   double sre[6][16];   // sigma_{mu nu} as 4x4 complex
@@ -524,6 +555,18 @@ __global__ void __launch_bounds__(64) k_build_clover(Geom g, int p, size_t nsU, 
               }
           }
     }
+  if (cc.open_bc) {
+    const int t = c[3];
+    for (int b = 0; b < 2; b++)
+      for (int k = 0; k < 36; k++) {
+        const bool dg = k / 6 == k % 6;
+        if (t == 0 || t == cc.T - 1) {
+          br[b][k] = dg ? cc.diag + cc.edge : 0.0;
+          bi[b][k] = 0.0;
+        } else if ((t == 1 || t == cc.T - 2) && dg)
+          br[b][k] += cc.cF1;
+      }
+  }
   for (int b = 0; b < 2; b++) {
     store_compact<T>(clov, g.half4, i4, b, br[b], bi[b]);
     inv6(br[b], bi[b]);
@@ -667,6 +710,7 @@ static void import_gauge_t(cgptb_fermion_operator* op, const cgptb_lattice* cons
     lc.goff[mu] = op->goff[mu];
     lc.gL[mu] = op->gL[mu];
   }
+  lc.open_bc = op->open_bc ? 1 : 0;
   size_t link_bytes = (size_t)op->g.half4 * 8 * 18 * sizeof(T);
   op->links_pad_valid = false;
   int threads = 128;
@@ -684,6 +728,10 @@ static void import_gauge_t(cgptb_fermion_operator* op, const cgptb_lattice* cons
   if (op->has_clover) {
     CloverCoef cc;
     cc.diag = op->p.mass + 1.0 + 3.0 * op->p.nu / op->p.xi_0;
+    cc.open_bc = op->open_bc ? 1 : 0;
+    cc.T = op->dims4[3];
+    cc.edge = -0.5 * op->p.csw_t;
+    cc.cF1 = op->p.cF - 1.0;
     // gamma matrices (lib/gpt/core/gamma.py:28-41) as (re,im) 4x4
     static const double gre[4][16] = {{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0},
                                       {0, 0, 0, -1, 0, 0, 1, 0, 0, 1, 0, 0, -1, 0, 0, 0},
@@ -813,7 +861,14 @@ static void twist_apply(const cgptb_lattice* in, cgptb_lattice* out, bool acc, d
   LAUNCH_CHECK();
 }
 
+static void op_mooee_impl(cgptb_fermion_operator* op, bool inverse, bool dag, bool acc, const cgptb_lattice* in, cgptb_lattice* out);
+
 void op_mooee(cgptb_fermion_operator* op, bool inverse, bool dag, bool acc, const cgptb_lattice* in, cgptb_lattice* out) {
+  op_mooee_impl(op, inverse, dag, acc, in, out);
+  apply_open_boundaries(op, out);
+}
+
+static void op_mooee_impl(cgptb_fermion_operator* op, bool inverse, bool dag, bool acc, const cgptb_lattice* in, cgptb_lattice* out) {
   if (op->type == CGPTB_MOBIUS) {
     if (inverse) {
       CGPTB_ASSERT(!acc);
@@ -1015,8 +1070,12 @@ int cgptb_create_fermion_operator(cgptb_fermion_operator** out, int optype, int 
       if (params->Ls < 1) CGPTB_ERR("mobius needs Ls >= 1");
       op->setup_mobius_tables();
     } else {
-      if (params->boundary_phases[6] == 0.0 && params->boundary_phases[7] == 0.0)
-        CGPTB_ERR("open boundary conditions (boundary_phases[3] == 0) are not implemented");
+      if (params->boundary_phases[6] == 0.0 && params->boundary_phases[7] == 0.0) {
+        // open boundary conditions in time (reference/wilson_clover.py:78-88: isotropic, csw_r == csw_t, cF given)
+        if (params->xi_0 != 1.0 || params->nu != 1.0 || params->csw_r != params->csw_t)
+          CGPTB_ERR("open boundary conditions need xi_0 = nu = 1 and csw_r = csw_t");
+        op->open_bc = true;
+      }
       if (params->xi_0 == 0.0) CGPTB_ERR("xi_0 must be non-zero");
       if (params->mu != 0.0 && (params->csw_r != 0.0 || params->csw_t != 0.0)) CGPTB_ERR("twisted mass with a clover term is not a GPT operator");
     }

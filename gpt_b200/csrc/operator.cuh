@@ -10,6 +10,7 @@ struct LinkCoef {
   double ph[8];   // boundary phases (re,im)
   int goff[4];    // global offset of the local lattice (multi-GPU decomposition)
   int gL[4];      // global extents
+  int open_bc;    // open boundary conditions in time: U_t on the global slices 0, T-2, T-1 is zero (see import_gauge_t)
 };
 }  // namespace cgptb
 
@@ -22,6 +23,7 @@ struct cgptb_fermion_operator {
   void* links[2] = {0, 0};      // per output parity: [half4][8][9] complex, -c_mu/2 and phases folded in
   void* links_pad[2] = {0, 0};  // the same links as [2 halves][site][304 B] for the TMA sweep kernel (dslash_tma.cu), built lazily
   bool links_pad_valid = false;
+  bool open_bc = false;         // boundary_phases[3] == 0: results vanish on the global time slices 0 and T-1
   bool has_clover = false;
   void* clov[2] = {0, 0};       // per parity: [72][half4] reals
   void* clov_inv[2] = {0, 0};
@@ -44,6 +46,7 @@ struct cgptb_fermion_operator {
 };
 
 namespace cgptb {
+void apply_open_boundaries(const cgptb_fermion_operator* op, cgptb_lattice* l);
 void op_dhop(cgptb_fermion_operator* op, bool dag, const cgptb_lattice* in, cgptb_lattice* out);
 void op_meooe(cgptb_fermion_operator* op, bool dag, const cgptb_lattice* in, cgptb_lattice* out);
 void op_mooee(cgptb_fermion_operator* op, bool inverse, bool dag, bool acc, const cgptb_lattice* in, cgptb_lattice* out);

@@ -22,9 +22,8 @@ def wilson_clover(U, params):
         params["Ls"] = params["n_rhs"]
     else:
         params["multi_rhs"] = False
-    if params["boundary_phases"][-1] == 0.0:
-        raise NotImplementedError("open boundary conditions are a SURVEY 8(f2) next row")
-    assert params["cF"] == 1.0  # forbid usage of cF without open bc
+    if params["boundary_phases"][-1] != 0.0:
+        assert params["cF"] == 1.0  # forbid usage of cF without open bc (wilson.py:142-143)
     return fine_operator("wilson_clover", U, params, otype=g.ot_vector_spin_color(4, 3))
 
 

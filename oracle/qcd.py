@@ -230,7 +230,13 @@ def dhop(V, psi, coef=(1.0, 1.0, 1.0, 1.0), dag=False, five_d=False):
 class wilson_clover:
     """
     g.qcd.fermion.wilson_clover(U, ...)  (lib/gpt/qcd/fermion/wilson.py:115-148, cgpt operators/wilson_clover.h)
-    periodic / phase boundary conditions (open bc & cF out of scope).
+    periodic / phase boundary conditions, and open boundary conditions in time (boundary_phases[3] == 0) with the boundary
+    improvement coefficient cF exactly as lib/gpt/qcd/fermion/reference/wilson_clover.py:78-125,179-220 does them: no hopping
+    across the boundary, clover term replaced by -csw_t/2 on the time slices 0 and T-1, (cF - 1) added on the slices 1 and T-2,
+    every operator result set to zero on the slices 0 and T-1 (lib/gpt/qcd/fermion/boundary_conditions.py:23-31).
+    Grid's operator (the one the reference fingerprints, tests/qcd/fermion_operators.py:356-364,383-386) is P D P with P the
+    projector on 0 < t < T-1: the hopping term also ignores what sits on the two boundary slices of its INPUT; this, not the
+    Python reference's one-sided mask, reproduces the golden number.
     """
 
     def __init__(self, U, kappa=None, mass=None, csw_r=0.0, csw_t=0.0, xi_0=1.0, nu=1.0,
@@ -238,7 +244,9 @@ class wilson_clover:
         if kappa is not None:
             assert mass is None
             mass = 1.0 / kappa / 2.0 - 4.0
-        assert boundary_phases[3] != 0.0
+        self.open_bc = boundary_phases[3] == 0.0
+        if self.open_bc:
+            assert xi_0 == 1.0 and nu == 1.0 and csw_r == csw_t  # reference/wilson_clover.py:80-88
         self.U = U
         self.dtype = U[0].dtype
         self.dims4 = U[0].shape[:4][::-1]
@@ -259,6 +267,18 @@ class wilson_clover:
                     cp = csw_t if nu_ == 3 else csw_r / xi_0
                     F = field_strength(Ud, mu, nu_)
                     cl += -0.5 * cp * np.einsum("ab,...ij->...abij", sigma(mu, nu_), F)
+            if self.open_bc:
+                T = cl.shape[0]
+                for t in (0, T - 1):
+                    cl[t] = 0.0
+                    for a in range(4):
+                        for i in range(3):
+                            cl[t, ..., a, a, i, i] = -0.5 * csw_t
+                if cF != 1.0:
+                    for t in (1, T - 2):
+                        for a in range(4):
+                            for i in range(3):
+                                cl[t, ..., a, a, i, i] += cF - 1.0
             for a in range(4):
                 for i in range(3):
                     cl[..., a, a, i, i] += self.diag
@@ -268,8 +288,15 @@ class wilson_clover:
             self.clover = self.clover.astype(self.dtype)
             self.clover_inv = self.clover_inv.astype(self.dtype)
 
+    def _bc(self, psi):
+        if self.open_bc:
+            psi = psi.copy()
+            psi[0] = 0.0
+            psi[-1] = 0.0
+        return psi
+
     def Dhop(self, psi, dag=False):
-        return dhop(self.V, psi, self.coef, dag)
+        return self._bc(dhop(self.V, self._bc(psi), self.coef, dag))
 
     def _site(self, mat, psi):
         sh = psi.shape
@@ -283,16 +310,16 @@ class wilson_clover:
         if self.mu != 0.0:
             return self._twist(psi, self.diag, -self.mu if dag else self.mu)
         if self.clover is None:
-            return psi.dtype.type(self.diag) * psi
-        return self._site(adj(self.clover) if dag else self.clover, psi)
+            return self._bc(psi.dtype.type(self.diag) * psi)
+        return self._bc(self._site(adj(self.clover) if dag else self.clover, psi))
 
     def MooeeInv(self, psi, dag=False):
         if self.mu != 0.0:
             den = self.diag**2 + self.mu**2
             return self._twist(psi, self.diag / den, (self.mu if dag else -self.mu) / den)
         if self.clover is None:
-            return psi.dtype.type(1.0 / self.diag) * psi
-        return self._site(adj(self.clover_inv) if dag else self.clover_inv, psi)
+            return self._bc(psi.dtype.type(1.0 / self.diag) * psi)
+        return self._bc(self._site(adj(self.clover_inv) if dag else self.clover_inv, psi))
 
     Mdiag = Mooee
 

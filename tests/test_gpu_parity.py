@@ -147,12 +147,14 @@ def _ops4(g, fields, params, precision):
 
 
 TWISTED = dict(mass=-1.8, mu=0.2, boundary_phases=[1.0, 1.0, 1.0, -1.0])  # tests/qcd/fermion_operators.py:365-369
+# open boundary conditions in time with the boundary improvement cF (tests/qcd/fermion_operators.py:356-364)
+OPEN = dict(kappa=0.13500, csw_r=1.978, csw_t=1.978, cF=1.3, xi_0=1, nu=1, isAnisotropic=False, boundary_phases=[1.0, 1.0, 1.0, 0.0])
 
 
 @pytest.mark.parametrize("precision", ["double", "single"])
-@pytest.mark.parametrize("name", ["wilson", "clover", "twisted"])
+@pytest.mark.parametrize("name", ["wilson", "clover", "twisted", "open"])
 def test_wilson_clover_full(g, fields, name, precision):
-    params = {"wilson": WILSON, "clover": CLOVER, "twisted": TWISTED}[name]
+    params = {"wilson": WILSON, "clover": CLOVER, "twisted": TWISTED, "open": OPEN}[name]
     grid, w, wo = _ops4(g, fields, params, precision)
     tol = TOL[precision]
     src_np = fields["srcw"].astype(grid.precision.complex_dtype)
@@ -168,7 +170,8 @@ def test_wilson_clover_full(g, fields, name, precision):
         dst = to_spinor(g, grid, fields["dstw"])
         golden = {"wilson": (-999.7564252326631 - 466.7758727463097j, -961.5053827614738 - 3468.430447866095j),
                   "clover": (-946.8714968698364 - 427.1253034080037j, -908.620454398646 - 3428.779878527792j),
-                  "twisted": (-5.665095757463064 + 373.96051873176737j, -440.5312395819657 - 1102.362512575698j)}[name]
+                  "twisted": (-5.665095757463064 + 373.96051873176737j, -440.5312395819657 - 1102.362512575698j),
+                  "open": (-1634.2615676797234 + 239.27037187495998j, -1239.3535155227526 - 1158.5295177146759j)}[name]
         X = g.inner_product(dst, g(w * src))
         assert abs(X - golden[0]) / abs(golden[0]) < 1e-13
         X = g.inner_product(dst, g(w.Mdiag * src))
@@ -176,9 +179,9 @@ def test_wilson_clover_full(g, fields, name, precision):
 
 
 @pytest.mark.parametrize("precision", ["double", "single"])
-@pytest.mark.parametrize("name", ["wilson", "clover", "twisted"])
+@pytest.mark.parametrize("name", ["wilson", "clover", "twisted", "open"])
 def test_wilson_clover_eo(g, fields, name, precision):
-    params = {"wilson": WILSON, "clover": CLOVER, "twisted": TWISTED}[name]
+    params = {"wilson": WILSON, "clover": CLOVER, "twisted": TWISTED, "open": OPEN}[name]
     grid, w, wo = _ops4(g, fields, params, precision)
     tol = TOL[precision]
     e = qcd.eo_ops(wo)

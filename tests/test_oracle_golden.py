@@ -107,6 +107,15 @@ def test_wilson_twisted_mass_fingerprints(fingerprint_fields):
     assert abs(a - b) / abs(a) < 1e-13
 
 
+def test_wilson_clover_open_bc_fingerprints(fingerprint_fields):
+    # tests/qcd/fermion_operators.py:356-364,383-386: open boundary conditions in time, cF = 1.3
+    f = fingerprint_fields
+    w = qcd.wilson_clover(f["Uw"], kappa=0.13500, csw_r=1.978, csw_t=1.978, cF=1.3, xi_0=1, nu=1, isAnisotropic=False,
+                          boundary_phases=[1.0, 1.0, 1.0, 0.0])
+    assert _close(qcd.inner_product(f["dstw"], w.M(f["srcw"])), -1634.2615676797234 + 239.27037187495998j)
+    assert _close(qcd.inner_product(f["dstw"], w.Mdiag(f["srcw"])), -1239.3535155227526 - 1158.5295177146759j)
+
+
 def test_mobius_fingerprints(fingerprint_fields):
     f = fingerprint_fields
     m = qcd.mobius(f["U"], **MOBIUS)
