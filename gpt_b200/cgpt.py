@@ -34,6 +34,8 @@ class fermion_params(ctypes.Structure):
         ("Ls", c_int),
         ("boundary_phases", c_double * 8),
         ("mu", c_double),
+        ("n_omega", c_int),
+        ("omega", c_double * 128),
     ]
 
 
@@ -344,6 +346,12 @@ def _params(p):
         v = p.get(k, None)
         setattr(fp, k, float(v) if v is not None else 0.0)
     fp.isAnisotropic = 1 if p.get("isAnisotropic", False) else 0
+    omega = p.get("omega", None) or []
+    if len(omega) > 64:
+        raise RuntimeError("zmobius supports Ls <= 64")
+    fp.n_omega = len(omega)
+    for i, w in enumerate(omega):
+        fp.omega[2 * i], fp.omega[2 * i + 1] = complex(w).real, complex(w).imag
     fp.Ls = int(p.get("Ls", 0) or 0)
     bp = p.get("boundary_phases", [1.0, 1.0, 1.0, 1.0])
     for i in range(4):
@@ -354,7 +362,8 @@ def _params(p):
 
 
 # wilson_twisted_mass is the Wilson operator with the parameter mu set (no clover term)
-_optypes = {"wilson_clover": WILSON_CLOVER, "wilson_twisted_mass": WILSON_CLOVER, "mobius": MOBIUS}
+# zmobius is the Moebius operator with the complex omega_s set
+_optypes = {"wilson_clover": WILSON_CLOVER, "wilson_twisted_mass": WILSON_CLOVER, "mobius": MOBIUS, "zmobius": MOBIUS}
 _precisions = {"single": SINGLE, "double": DOUBLE}
 
 

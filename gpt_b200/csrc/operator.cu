@@ -4,6 +4,7 @@
 //   Dhop/DhopEO(+Dag), Meooe(+Dag), Mooee(+Dag), MooeeInv(+Dag), M, Mdag, Mdiag, Dminus(+Dag),
 //   Import/Export{Physical,Unphysical}Fermion{Source,Solution}.
 #include <stdlib.h>
+#include <complex>
 #include "operator.cuh"
 #include "dslash.cuh"
 
@@ -224,7 +225,74 @@ __global__ void __launch_bounds__(128) k_s_dense(size_t n, int ls, const T* __re
   store_spinor(out, stride, tid, r);
 }
 
+// zMoebius: dense complex Ls x Ls chirality blocks, out_s (+)= sum_s' Mp[s][s'] P+ psi_s' + Mm[s][s'] P- psi_s'.  Every
+// s-operator of the zMoebius action goes through this one kernel (the tridiagonal structure is not exploited yet).
+template <typename T, bool ACC>
+__global__ void __launch_bounds__(128) k_s_dense_c(size_t n, int ls, const T* __restrict__ in, T* __restrict__ out, size_t stride,
+                                                   const T* __restrict__ Mp, const T* __restrict__ Mm) {
+  size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= n) return;
+  size_t i4 = tid / ls;
+  int s = (int)(tid - i4 * ls);
+  T r[24];
+  if (ACC)
+    load_spinor_rw(out, stride, tid, r);
+  else {
+#pragma unroll
+    for (int k = 0; k < 24; k++) r[k] = 0;
+  }
+  for (int sp = 0; sp < ls; sp++) {
+    const T pr = Mp[2 * (s * ls + sp)], pi = Mp[2 * (s * ls + sp) + 1];
+    const T mr = Mm[2 * (s * ls + sp)], mi = Mm[2 * (s * ls + sp) + 1];
+    if (pr == 0 && pi == 0 && mr == 0 && mi == 0) continue;  // uniform over the threads that share s
+    T v[24];
+    load_spinor(in, stride, i4 * ls + sp, v);
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+      r[2 * c] += pr * v[2 * c] - pi * v[2 * c + 1];
+      r[2 * c + 1] += pr * v[2 * c + 1] + pi * v[2 * c];
+    }
+#pragma unroll
+    for (int c = 6; c < 12; c++) {
+      r[2 * c] += mr * v[2 * c] - mi * v[2 * c + 1];
+      r[2 * c + 1] += mr * v[2 * c + 1] + mi * v[2 * c];
+    }
+  }
+  store_spinor(out, stride, tid, r);
+}
+
+void op_s_z(cgptb_fermion_operator* op, int zkind, bool dag, bool acc, const cgptb_lattice* in, cgptb_lattice* out) {
+  op->check_field(in);
+  op->check_field(out);
+  CGPTB_ASSERT(op->zmobius && op->z_tab && in->sites == out->sites && in->data != out->data);
+  if (!acc) out->cb = in->cb;
+  const int ls = op->Ls;
+  const size_t n = in->sites;
+  const unsigned blocks = (unsigned)((n + 127) / 128);
+  const size_t blk = (size_t)ls * ls * 2;
+  const size_t off = (size_t)(zkind * 2 + (dag ? 1 : 0)) * 2 * blk;
+  if (op->prec == CGPTB_SINGLE) {
+    const float* m = (const float*)op->z_tab + off;
+    if (acc)
+      k_s_dense_c<float, true><<<blocks, 128, 0, g_stream>>>(n, ls, (const float*)in->data, (float*)out->data, n, m, m + blk);
+    else
+      k_s_dense_c<float, false><<<blocks, 128, 0, g_stream>>>(n, ls, (const float*)in->data, (float*)out->data, n, m, m + blk);
+  } else {
+    const double* m = (const double*)op->z_tab + off;
+    if (acc)
+      k_s_dense_c<double, true><<<blocks, 128, 0, g_stream>>>(n, ls, (const double*)in->data, (double*)out->data, n, m, m + blk);
+    else
+      k_s_dense_c<double, false><<<blocks, 128, 0, g_stream>>>(n, ls, (const double*)in->data, (double*)out->data, n, m, m + blk);
+  }
+  LAUNCH_CHECK();
+}
+
 void op_s_tridiag(cgptb_fermion_operator* op, int kind, bool dag, bool acc, const cgptb_lattice* in, cgptb_lattice* out) {
+  if (op->zmobius) {
+    CGPTB_ASSERT(kind == 0 || kind == 2);
+    op_s_z(op, kind == 0 ? ZK_A : ZK_EE, dag, acc, in, out);
+    return;
+  }
   op->check_field(in);
   op->check_field(out);
   CGPTB_ASSERT(in->sites == out->sites && in->data != out->data);
@@ -251,6 +319,10 @@ void op_s_tridiag(cgptb_fermion_operator* op, int kind, bool dag, bool acc, cons
 }
 
 void op_s_dense(cgptb_fermion_operator* op, bool dag, const cgptb_lattice* in, cgptb_lattice* out) {
+  if (op->zmobius) {
+    op_s_z(op, ZK_EEINV, dag, false, in, out);
+    return;
+  }
   op->check_field(in);
   op->check_field(out);
   CGPTB_ASSERT(in->sites == out->sites && in->data != out->data);
@@ -641,7 +713,96 @@ static void upload(void** dev, const std::vector<double>& h) {
 }
 
 // coefficient tables of the s-direction operators; S5 as in SURVEY Appendix A.2 / tests/qcd/domain_wall.py:309-341
+// zMoebius: all s-operators as dense complex chirality blocks, built like the oracle does (oracle/qcd.py zmobius._AB)
+static void setup_zmobius_tables(cgptb_fermion_operator* op) {
+  typedef std::complex<double> cd;
+  const int ls = op->Ls;
+  const cgptb_fermion_params& p = op->p;
+  std::vector<cd> bs(ls), cs(ls);
+  for (int s = 0; s < ls; s++) {
+    const cd om(p.omega[2 * s], p.omega[2 * s + 1]);
+    bs[s] = 0.5 * ((p.b + p.c) / om + (p.b - p.c));  // lib/gpt/qcd/fermion/zmobius.py:33
+    cs[s] = 0.5 * ((p.b + p.c) / om - (p.b - p.c));
+  }
+  const size_t nn = (size_t)ls * ls;
+  auto S5 = [&](int chir) {  // chir 0: P+ block, 1: P- block
+    std::vector<cd> S(nn, cd(0));
+    for (int s = 0; s < ls; s++) {
+      if (chir == 0 && s >= 1) S[s * ls + s - 1] = 1.0;
+      if (chir == 1 && s + 1 < ls) S[s * ls + s + 1] = 1.0;
+    }
+    if (chir == 0)
+      S[0 * ls + ls - 1] += -p.mass_plus;
+    else
+      S[(ls - 1) * ls + 0] += -p.mass_minus;
+    return S;
+  };
+  auto inverse = [&](std::vector<cd> a) {
+    std::vector<cd> b(nn, cd(0));
+    for (int i = 0; i < ls; i++) b[i * ls + i] = 1.0;
+    for (int col = 0; col < ls; col++) {
+      int piv = col;
+      for (int r = col + 1; r < ls; r++)
+        if (std::abs(a[r * ls + col]) > std::abs(a[piv * ls + col])) piv = r;
+      if (std::abs(a[piv * ls + col]) == 0.0) CGPTB_ERR("zmobius: Mooee is singular");
+      for (int k = 0; k < ls; k++) {
+        std::swap(a[col * ls + k], a[piv * ls + k]);
+        std::swap(b[col * ls + k], b[piv * ls + k]);
+      }
+      const cd d = 1.0 / a[col * ls + col];
+      for (int k = 0; k < ls; k++) {
+        a[col * ls + k] *= d;
+        b[col * ls + k] *= d;
+      }
+      for (int r = 0; r < ls; r++) {
+        if (r == col) continue;
+        const cd f = a[r * ls + col];
+        if (f == cd(0)) continue;
+        for (int k = 0; k < ls; k++) {
+          a[r * ls + k] -= f * a[col * ls + k];
+          b[r * ls + k] -= f * b[col * ls + k];
+        }
+      }
+    }
+    return b;
+  };
+  std::vector<double> tab((size_t)ZK_COUNT * 2 * 2 * nn * 2, 0.0);
+  for (int chir = 0; chir < 2; chir++) {
+    const std::vector<cd> S = S5(chir);
+    std::vector<cd> M[ZK_COUNT];
+    for (int k = 0; k < ZK_COUNT; k++) M[k].assign(nn, cd(0));
+    for (int s = 0; s < ls; s++)
+      for (int t = 0; t < ls; t++) {
+        const cd id = s == t ? 1.0 : 0.0;
+        const cd A = bs[s] * id + cs[s] * S[s * ls + t];
+        M[ZK_A][s * ls + t] = A;
+        M[ZK_EE][s * ls + t] = (4.0 - p.M5) * A + id - S[s * ls + t];
+        M[ZK_DM1][s * ls + t] = (1.0 - cs[s] * (4.0 - p.M5)) * id;
+        M[ZK_DM2][s * ls + t] = -cs[s] * id;
+      }
+    M[ZK_EEINV] = inverse(M[ZK_EE]);
+    for (int k = 0; k < ZK_COUNT; k++)
+      for (int dag = 0; dag < 2; dag++) {
+        double* o = &tab[((size_t)(k * 2 + dag) * 2 + chir) * nn * 2];
+        for (int s = 0; s < ls; s++)
+          for (int t = 0; t < ls; t++) {
+            const cd v = dag ? std::conj(M[k][t * ls + s]) : M[k][s * ls + t];
+            o[2 * (s * ls + t)] = v.real();
+            o[2 * (s * ls + t) + 1] = v.imag();
+          }
+      }
+  }
+  if (op->prec == CGPTB_SINGLE)
+    upload<float>(&op->z_tab, tab);
+  else
+    upload<double>(&op->z_tab, tab);
+}
+
 void cgptb_fermion_operator::setup_mobius_tables() {
+  if (zmobius) {
+    setup_zmobius_tables(this);
+    return;
+  }
   int ls = Ls;
   double b = p.b, c = p.c, mp = p.mass_plus, mm = p.mass_minus;
   double bee = b * (4.0 - p.M5) + 1.0, cee = 1.0 - c * (4.0 - p.M5);
@@ -969,6 +1130,11 @@ static void op_dminus(cgptb_fermion_operator* op, bool dag, const cgptb_lattice*
   CGPTB_ASSERT(in->cb == CGPTB_FULL && out->cb == CGPTB_FULL);
   cgptb_lattice* t = op->tmp(1, CGPTB_FULL);
   op_dhop(op, dag, in, t);
+  if (op->zmobius) {  // psi_s - c_s D_W psi_s with complex c_s (conjugated for the adjoint)
+    op_s_z(op, ZK_DM1, dag, false, in, out);
+    op_s_z(op, ZK_DM2, dag, true, t, out);
+    return;
+  }
   double coef[4] = {1.0 - op->p.c * (4.0 - op->p.M5), 0.0, -op->p.c, 0.0};
   const cgptb_lattice* a[2] = {in, t};
   blas_lc(out, 0, 2, coef, a);
@@ -1068,6 +1234,10 @@ int cgptb_create_fermion_operator(cgptb_fermion_operator** out, int optype, int 
   try {
     if (optype == CGPTB_MOBIUS) {
       if (params->Ls < 1) CGPTB_ERR("mobius needs Ls >= 1");
+      if (params->n_omega > 0) {
+        if (params->n_omega != params->Ls || params->Ls > 64) CGPTB_ERR("zmobius needs Ls = len(omega) <= 64");
+        op->zmobius = true;
+      }
       op->setup_mobius_tables();
     } else {
       if (params->boundary_phases[6] == 0.0 && params->boundary_phases[7] == 0.0) {
@@ -1124,6 +1294,7 @@ int cgptb_delete_fermion_operator(cgptb_fermion_operator* op) {
     }
     if (op->s_coef) cudaFree(op->s_coef);
     if (op->s_inv) cudaFree(op->s_inv);
+    if (op->z_tab) cudaFree(op->z_tab);
     for (int i = 0; i < 4; i++) {
       if (op->tmp_full[i]) cgptb_delete_lattice(op->tmp_full[i]);
       if (op->tmp_half[i]) cgptb_delete_lattice(op->tmp_half[i]);

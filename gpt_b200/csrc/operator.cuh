@@ -29,6 +29,8 @@ struct cgptb_fermion_operator {
   void* clov_inv[2] = {0, 0};
   void* s_coef = 0;             // Moebius tridiagonal tables [3 kinds][2 dag][5][Ls]
   void* s_inv = 0;              // dense MooeeInv blocks [P+, P-, P+^T, P-^T][Ls][Ls]
+  bool zmobius = false;         // complex, s-dependent coefficients (p.n_omega > 0)
+  void* z_tab = 0;              // zMoebius: dense complex blocks [kind 5][dag 2][P+, P-][Ls][Ls][re, im]
   cgptb_lattice* tmp_full[4] = {0, 0, 0, 0};
   cgptb_lattice* tmp_half[4] = {0, 0, 0, 0};
   // multi-GPU decomposition (halo.cu); g.comm_mask marks the split directions
@@ -52,6 +54,9 @@ void op_meooe(cgptb_fermion_operator* op, bool dag, const cgptb_lattice* in, cgp
 void op_mooee(cgptb_fermion_operator* op, bool inverse, bool dag, bool acc, const cgptb_lattice* in, cgptb_lattice* out);
 void op_s_tridiag(cgptb_fermion_operator* op, int kind, bool dag, bool acc, const cgptb_lattice* in, cgptb_lattice* out);
 void op_s_dense(cgptb_fermion_operator* op, bool dag, const cgptb_lattice* in, cgptb_lattice* out);
+// zMoebius: kind 0 = b_s + c_s S5, 1 = Mooee, 2 = MooeeInv, 3 = 1 - c_s (4 - M5), 4 = -c_s (the two pieces of Dminus)
+enum { ZK_A = 0, ZK_EE = 1, ZK_EEINV = 2, ZK_DM1 = 3, ZK_DM2 = 4, ZK_COUNT = 5 };
+void op_s_z(cgptb_fermion_operator* op, int zkind, bool dag, bool acc, const cgptb_lattice* in, cgptb_lattice* out);
 void op_apply(cgptb_fermion_operator* op, int opcode, const cgptb_lattice* src, cgptb_lattice* dst);
 // sweep.cu: fused fifth-dimension operators; T = (b + c S5)(bee - cee S5)^-1 = Meooe5D o MooeeInv
 enum { SWEEP_T = 0, SWEEP_TDAG = 1, SWEEP_MINV = 2, SWEEP_MINVDAG = 3 };

@@ -47,7 +47,7 @@ void op_schur_two(cgptb_fermion_operator* op, bool dag, const cgptb_lattice* in,
   cgptb_lattice* tc1 = op->tmp(3, C);
   static int no_sweep = getenv("CGPTB_NO_SWEEP") ? 1 : 0;
   bool done_dot = false;
-  if (op->type == CGPTB_MOBIUS && !no_sweep && sweep_supported(op->Ls)) {
+  if (op->type == CGPTB_MOBIUS && !op->zmobius && !no_sweep && sweep_supported(op->Ls)) {
     if (dhop_fusable(op)) {
       double* partial = dot ? blas_partial_scratch(dhop_tile_blocks(op)) : 0;
       if (!dag) {
@@ -132,7 +132,7 @@ int cgptb_cg_eo2_ne(cgptb_fermion_operator* op, cgptb_lattice* psi, const cgptb_
     }
   } guard{all};
   static int no_upd = getenv("CGPTB_NO_FUSED_UPDATE") ? 1 : 0;
-  bool fuse_update = !no_upd && dhop_fusable(op) && sweep_supported(op->Ls);
+  bool fuse_update = !no_upd && !op->zmobius && dhop_fusable(op) && sweep_supported(op->Ls);
   for (int i = 0; i < (fuse_update ? 5 : 4); i++)
     if (cgptb_create_lattice(all[i], op->dims4, op->Ls, op->prec, CGPTB_OT_VSPINCOLOR, src->cb)) CGPTB_ERR("%s", cgptb_last_error());
 

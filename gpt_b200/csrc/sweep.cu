@@ -222,7 +222,7 @@ bool op_s_sweep(cgptb_fermion_operator* op, int mode, const cgptb_lattice* in, c
   op->check_field(in);
   op->check_field(out);
   CGPTB_ASSERT(op->type == CGPTB_MOBIUS && in->sites == out->sites);
-  if (!sweep_supported(op->Ls)) return false;
+  if (op->zmobius || !sweep_supported(op->Ls)) return false;  // zMoebius: complex coefficients, dense kernel instead
   bool ok = op->prec == CGPTB_SINGLE ? sweep_t<float>(op, mode, in, out) : sweep_t<double>(op, mode, in, out);
   if (ok) out->cb = in->cb;
   return ok;

@@ -30,3 +30,13 @@ class mobius_class_operator(fine_operator):
 def mobius(U, params):
     params = copy.deepcopy(params)
     return mobius_class_operator("mobius", U, params, otype=g.ot_vector_spin_color(4, 3))
+
+
+@g.params_convention(omega=None, mass=None, mass_plus=None, mass_minus=None, b=None, c=None, M5=None, boundary_phases=None)
+def zmobius(U, params):
+    """g.qcd.fermion.zmobius (lib/gpt/qcd/fermion/zmobius.py:62-74): Moebius with complex, s-dependent coefficients
+    b_s, c_s = 1/2 ((b + c) / omega_s +- (b - c)); Ls = len(omega)"""
+    params = copy.deepcopy(params)
+    params["omega"] = [complex(w) for w in params["omega"]]
+    params["Ls"] = len(params["omega"])
+    return mobius_class_operator("zmobius", U, params, otype=g.ot_vector_spin_color(4, 3))

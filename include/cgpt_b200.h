@@ -146,6 +146,9 @@ typedef struct {
   double boundary_phases[8];
   /* wilson_twisted_mass (lib/cgpt/lib/operators/wilson_twisted_mass.h): Mooee = (4 + mass) + i mu gamma_5; 0 = untwisted */
   double mu;
+  /* zmobius (lib/cgpt/lib/operators/zmobius.h:20-56): n_omega = Ls complex omega_s (re,im); 0 = plain Moebius */
+  int n_omega;
+  double omega[2 * 64];
 } cgptb_fermion_params;
 
 /* cgpt.create_fermion_operator(optype, prec, params): U = 4 colour-matrix lattices on the full 4d grid */

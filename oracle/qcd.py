@@ -386,8 +386,8 @@ class mobius:
     def _sop(self, psi, Ap, Am):
         """(out)_s = sum_s' Ap[s,s'] P+ psi_s' + Am[s,s'] P- psi_s'  ; psi [T,Z,Y,X,Ls,4,3]"""
         out = np.empty_like(psi)
-        Ap = Ap.astype(psi.real.dtype)
-        Am = Am.astype(psi.real.dtype)
+        Ap = Ap.astype(psi.dtype if np.iscomplexobj(Ap) else psi.real.dtype)
+        Am = Am.astype(psi.dtype if np.iscomplexobj(Am) else psi.real.dtype)
         out[..., 0:2, :] = np.einsum("st,...tac->...sac", Ap, psi[..., 0:2, :])
         out[..., 2:4, :] = np.einsum("st,...tac->...sac", Am, psi[..., 2:4, :])
         return out
@@ -404,7 +404,7 @@ class mobius:
             Ap = np.linalg.inv(self.bee * I - self.cee * self.Sp)
             Am = np.linalg.inv(self.bee * I - self.cee * self.Sm)
         if dag:
-            Ap, Am = Ap.T.copy(), Am.T.copy()
+            Ap, Am = np.conj(Ap.T).copy(), np.conj(Am.T).copy()
         return Ap, Am
 
     def S(self, kind, psi, dag=False):
@@ -453,6 +453,44 @@ class mobius:
 
     def ExportPhysicalFermionSource(self, psi):  # 2015
         return spin_mul(Pplus, psi[..., 0, :, :]) + spin_mul(Pminus, psi[..., self.Ls - 1, :, :])
+
+
+class zmobius(mobius):
+    """
+    g.qcd.fermion.zmobius(U, mass, M5, b, c, omega, boundary_phases)  (lib/gpt/qcd/fermion/zmobius.py:24-74; cgpt
+    operators/zmobius.h:20-56 -> Grid's ZMobiusFermion): the Moebius operator with complex, s-dependent coefficients
+        b_s = 1/2 ((b + c) / omega_s + (b - c)),   c_s = 1/2 ((b + c) / omega_s - (b - c))      (zmobius.py:33),
+    M = D_W (diag(b_s) + diag(c_s) S5) + (1 - S5); Mooee = (4 - M5)(diag(b_s) + diag(c_s) S5) + (1 - S5), i.e. Grid's
+    bee_s = b_s (4 - M5) + 1, cee_s = 1 - c_s (4 - M5); Dminus psi_s = psi_s - c_s D_W psi_s.  Daggers are the conjugate
+    transposes.  Pinned by the reference's fingerprints tests/qcd/fermion_operators.py:397-426.
+    """
+
+    def __init__(self, U, omega, mass=None, mass_plus=None, mass_minus=None, M5=None, b=None, c=None, boundary_phases=(1, 1, 1, 1)):
+        super().__init__(U, mass=mass, mass_plus=mass_plus, mass_minus=mass_minus, M5=M5, b=b, c=c, Ls=len(omega),
+                         boundary_phases=boundary_phases)
+        om = np.asarray(omega, dtype=np.complex128)
+        self.bs = 0.5 * ((b + c) / om + (b - c))
+        self.cs = 0.5 * ((b + c) / om - (b - c))
+
+    def _AB(self, kind, dag):
+        I = np.identity(self.Ls, dtype=np.complex128)
+        Db, Dc = np.diag(self.bs), np.diag(self.cs)
+        A = [Db + Dc @ S for S in (self.Sp, self.Sm)]
+        B = [I - S for S in (self.Sp, self.Sm)]
+        if kind == "A":
+            Ap, Am = A
+        elif kind == "B":
+            Ap, Am = B
+        else:
+            ee = [(4.0 - self.M5) * a + bb for a, bb in zip(A, B)]
+            Ap, Am = ee if kind == "ee" else [np.linalg.inv(e) for e in ee]
+        if dag:
+            Ap, Am = np.conj(Ap.T).copy(), np.conj(Am.T).copy()
+        return Ap, Am
+
+    def Dminus(self, psi, dag=False):
+        cs = (np.conj(self.cs) if dag else self.cs).astype(psi.dtype).reshape((self.Ls, 1, 1))
+        return psi - cs * self.DW(psi, dag)
 
 
 # ------------------------------------------------------------------------------------------------

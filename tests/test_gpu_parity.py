@@ -634,3 +634,65 @@ def test_wilson_multi_rhs_block_solve(g):
         assert rel(from_spinor(dst[i], cols[i]), ref) < 1e-8, i
         r = g(op1 * dst[i] - src[i])
         assert (g.norm2(r) / g.norm2(src[i])) ** 0.5 < 1e-8
+
+
+# ---------------------------------------------------------------------------------------------------------
+# zMoebius (complex, s-dependent coefficients): every opcode against the oracle, the reference's fingerprints
+# (tests/qcd/fermion_operators.py:397-426) from the product's own random fields, eo2_ne CG
+# ---------------------------------------------------------------------------------------------------------
+ZMOBIUS = dict(
+    mass=0.08, M5=1.8, b=1.0, c=0.0, boundary_phases=[1.0, 1.0, 1.0, -1.0],
+    omega=[0.17661651536320583 + 1j * (0.14907774771612217), 0.23027432016909377 + 1j * (-0.03530801572584271),
+           0.3368765581549033 + 1j * (0), 0.7305711010541054 + 1j * (0), 1.1686138337986505 + 1j * (0.3506492418109086),
+           1.1686138337986505 + 1j * (-0.3506492418109086), 0.994175013717952 + 1j * (0), 0.5029903152251229 + 1j * (0),
+           0.23027432016909377 + 1j * (0.03530801572584271), 0.17661651536320583 + 1j * (-0.14907774771612217)])
+
+
+@pytest.mark.parametrize("precision", ["double", "single"])
+def test_zmobius(g, precision):
+    p = prec_of(g, precision)
+    tol = TOL[precision]
+    grid = g.grid(DIMS, p)
+    rng = g.random("finger_print")
+    orng = oracle_random("finger_print")
+    tag = None if precision == "double" else precision
+    U = g.qcd.gauge.random(grid, rng)
+    Uo = qcd.gauge_random(orng, DIMS, precision=precision)
+    m = g.qcd.fermion.zmobius(U, dict(ZMOBIUS))
+    mo = qcd.zmobius(Uo, **ZMOBIUS)
+    src5, dst5 = rng.cnormal(g.vspincolor(m.F_grid)), rng.cnormal(g.vspincolor(m.F_grid))
+    src4 = rng.cnormal(g.vspincolor(grid))
+    d5 = [10] + DIMS
+    s5 = orng.cnormal(d5, (4, 3), grid_tag=tag).astype(p.complex_dtype)
+    orng.cnormal(d5, (4, 3), grid_tag=tag)
+    s4 = orng.cnormal(DIMS, (4, 3), grid_tag=tag).astype(p.complex_dtype)
+    assert rel(src5[:], sites(s5, 2)) < (1e-13 if precision == "double" else 1e-6)
+    for i, (op, ref) in enumerate([
+        (m, mo.M(s5)), (m.adj(), mo.Mdag(s5)), (m.Mdiag, mo.Mdiag(s5)), (m.Dhop, mo.Dhop(s5)),
+        (m.Dminus, mo.Dminus(s5)), (m.Dminus.adj(), mo.Dminus(s5, dag=True)),
+    ]):
+        assert rel(from_spinor(g(op * src5), s5), ref) < tol, i
+    assert rel(from_spinor(g(m.ImportPhysicalFermionSource * src4), s5), mo.ImportPhysicalFermionSource(s4)) < tol
+    assert rel(from_spinor(g(m.ExportPhysicalFermionSolution * src5), s4), mo.ExportPhysicalFermionSolution(s5)) < tol
+    e = qcd.eo_ops(mo)
+    for cb in [g.even, g.odd]:
+        half_np = e.proj(s5, cb.tag)
+        half = to_spinor(g, m.F_grid_eo, s5, cb)
+        for j, (op, ref) in enumerate([
+            (m.Meooe, e.Meooe(half_np, cb.tag)), (m.Meooe.adj(), e.Meooe(half_np, cb.tag, dag=True)),
+            (m.Mooee, e.Mooee(half_np)), (m.Mooee.adj(), e.Mooee(half_np, dag=True)),
+            (m.Mooee.inv(), e.MooeeInv(half_np)), (m.Mooee.adj().inv(), e.MooeeInv(half_np, dag=True)),
+        ]):
+            assert rel(from_spinor(g(op * half), s5), ref) < tol, (cb, j)
+    if precision == "double":
+        for op, s, ref in [(m, src5, -2424.048033434305 + 10557.661684178218j), (m.Mdiag, src5, 2643.396577965267 + 6550.259431381319j),
+                           (m.ImportPhysicalFermionSource, src4, 4064.7879718582053 - 1357.0856808000196j)]:
+            X = g.inner_product(dst5, g(op * s))
+            assert abs(X - ref) / abs(ref) < 1e-13
+        # eo2_ne CG: true residual of the full system
+        inv = g.algorithms.inverter
+        cg = inv.cg(eps=1e-8, maxiter=2000)
+        slv = inv.preconditioned(g.qcd.fermion.preconditioner.eo2_ne(), cg)(m)
+        x = g(slv * src5)
+        r = g(m * x - src5)
+        assert (g.norm2(r) / g.norm2(src5)) ** 0.5 < 1e-6

@@ -116,6 +116,37 @@ def test_wilson_clover_open_bc_fingerprints(fingerprint_fields):
     assert _close(qcd.inner_product(f["dstw"], w.Mdiag(f["srcw"])), -1239.3535155227526 - 1158.5295177146759j)
 
 
+ZMOBIUS = dict(
+    mass=0.08, M5=1.8, b=1.0, c=0.0, boundary_phases=[1.0, 1.0, 1.0, -1.0],
+    omega=[0.17661651536320583 + 1j * (0.14907774771612217), 0.23027432016909377 + 1j * (-0.03530801572584271),
+           0.3368765581549033 + 1j * (0), 0.7305711010541054 + 1j * (0), 1.1686138337986505 + 1j * (0.3506492418109086),
+           1.1686138337986505 + 1j * (-0.3506492418109086), 0.994175013717952 + 1j * (0), 0.5029903152251229 + 1j * (0),
+           0.23027432016909377 + 1j * (0.03530801572584271), 0.17661651536320583 + 1j * (-0.14907774771612217)])
+
+
+def test_zmobius_fingerprints():
+    # tests/qcd/fermion_operators.py:397-426; draw order of the reference's test: U, then src/dst on F_grid (Ls = 10), U_grid
+    dims = [8, 8, 8, 16]
+    rng = random("finger_print")
+    U = qcd.gauge_random(rng, dims)
+    d5 = [10] + dims
+    src5, dst5 = rng.cnormal(d5, (4, 3)), rng.cnormal(d5, (4, 3))
+    src4 = rng.cnormal(dims, (4, 3))
+    m = qcd.zmobius(U, **ZMOBIUS)
+    assert _close(qcd.inner_product(dst5, m.M(src5)), -2424.048033434305 + 10557.661684178218j)
+    assert _close(qcd.inner_product(dst5, m.Mdiag(src5)), 2643.396577965267 + 6550.259431381319j)
+    assert _close(qcd.inner_product(dst5, m.ImportPhysicalFermionSource(src4)), 4064.7879718582053 - 1357.0856808000196j)
+    # structure: adjoints and inverses
+    a, b = qcd.inner_product(dst5, m.M(src5)), qcd.inner_product(m.Mdag(dst5), src5)
+    assert abs(a - b) / abs(a) < 1e-13
+    x = m.MooeeInv(m.Mooee(src5))
+    assert np.linalg.norm(x - src5) / np.linalg.norm(src5) < 1e-13
+    x = m.MooeeInv(m.Mooee(src5, dag=True), dag=True)
+    assert np.linalg.norm(x - src5) / np.linalg.norm(src5) < 1e-13
+    a, b = qcd.inner_product(dst5, m.Dminus(src5)), qcd.inner_product(m.Dminus(dst5, dag=True), src5)
+    assert abs(a - b) / abs(a) < 1e-13
+
+
 def test_mobius_fingerprints(fingerprint_fields):
     f = fingerprint_fields
     m = qcd.mobius(f["U"], **MOBIUS)
