@@ -577,6 +577,13 @@ def inner_product_norm2(a, b):
     return a.grid.globalsum(ip), a.grid.globalsum(n2)
 
 
+def scale_per_coordinate(d, s, a, dim):
+    """d = a[x_dim] * s (lib/gpt/core/transform.py:210-214)"""
+    if isinstance(s, expr):
+        s = eval(s)
+    cgpt.lattice_scale_per_coordinate(d.obj, s.obj, a, dim)
+
+
 def axpy(d, a, x, y):
     cgpt.lattice_axpy(d.obj, a, x.obj, y.obj)
 

@@ -340,11 +340,65 @@ __global__ void __launch_bounds__(BT) k_slice_dot(Geom g, size_t nsites, const T
   }
 }
 
+
+// d = a[x_dim] * s for every complex component (gpt.scale_per_coordinate, lib/gpt/core/transform.py:210-214 ->
+// cgpt.lattice_scale_per_coordinate): one thread per (component, site), the coordinate is recovered from the device site index
+template <typename T>
+__global__ void k_scale_per_coordinate(Geom g, int cb, int ls, int nd, int dim, int otype, int cpb, size_t nsites, const T* __restrict__ src,
+                                       T* __restrict__ dst, const double* __restrict__ a) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nsites * otype) return;
+  const int c = (int)(idx / nsites);
+  const size_t j = idx - (size_t)c * nsites;
+  const size_t per = (size_t)g.half4 * ls;
+  int p = cb;
+  size_t rem = j;
+  if (cb == CGPTB_FULL) {
+    p = j >= per ? 1 : 0;
+    rem = j - (size_t)p * per;
+  }
+  const int i4 = (int)(rem / ls);
+  const int s = (int)(rem - (size_t)i4 * ls);
+  int co[5];
+  co[0] = s;
+  cb_coords(g, p, i4, co[1], co[2], co[3], co[4]);
+  const int x = nd == 5 ? co[dim] : co[dim + 1];
+  const T ar = (T)a[2 * x], ai = (T)a[2 * x + 1];
+  const size_t o = elem_offset<T>(nsites, j, c, cpb);
+  const T re = src[o], im = src[o + 1];
+  dst[o] = ar * re - ai * im;
+  dst[o + 1] = ar * im + ai * re;
+}
+
 }  // namespace cgptb
 
 using namespace cgptb;
 
 extern "C" {
+
+int cgptb_lattice_scale_per_coordinate(cgptb_lattice* d, const cgptb_lattice* s, const double* a_re_im, int n, int dim) {
+  CGPTB_API_BEGIN
+  CGPTB_ASSERT(d && s && a_re_im && same_shape(d, s));
+  const int nd = s->Ls > 0 ? 5 : 4;
+  CGPTB_ASSERT(dim >= 0 && dim < nd);
+  const int ext = (nd == 5 && dim == 0) ? s->Ls : s->dims4[dim - (nd - 4)];
+  if (n != ext) CGPTB_ERR("scale_per_coordinate: %d factors for a dimension of extent %d", n, ext);
+  d->cb = s->cb;
+  double* tab = reduce_scratch((size_t)sm_count() * 8 * 3 + 8 + 2 * (size_t)n + 16) + (size_t)sm_count() * 8 * 3 + 16;
+  CUDA_CHECK(cudaMemcpyAsync(tab, a_re_im, 2 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+  CUDA_CHECK(cudaStreamSynchronize(g_stream));  // the host array may be a temporary of the caller
+  Geom g = make_geom(s->dims4);
+  const size_t total = s->sites * (size_t)s->otype;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  if (s->prec == CGPTB_SINGLE)
+    k_scale_per_coordinate<float><<<blocks, 256, 0, g_stream>>>(g, s->cb, s->ls(), nd, dim, s->otype, s->cpb(), s->sites, (const float*)s->data,
+                                                                (float*)d->data, tab);
+  else
+    k_scale_per_coordinate<double><<<blocks, 256, 0, g_stream>>>(g, s->cb, s->ls(), nd, dim, s->otype, s->cpb(), s->sites,
+                                                                 (const double*)s->data, (double*)d->data, tab);
+  LAUNCH_CHECK();
+  CGPTB_API_END
+}
 
 int cgptb_lattice_axpy(cgptb_lattice* r, double a_re, double a_im, const cgptb_lattice* x, const cgptb_lattice* y) {
   CGPTB_API_BEGIN

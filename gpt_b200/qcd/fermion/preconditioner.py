@@ -23,3 +23,19 @@ def eo2_ne(params):
         )
 
     return instantiate
+
+
+@params_convention(parity=None)
+def eo2_kappa_ne(params):
+    """eo2_ne of the kappa-rescaled Schur complement V Mpc V^-1, V = op.kappa() (zMoebius; even_odd_sites.py:75-89)"""
+    parity = params["parity"] if params["parity"] is not None else g.odd
+
+    def instantiate(op):
+        return g.algorithms.preconditioner.normal_equation(
+            g.algorithms.preconditioner.similarity_transformation(
+                g.algorithms.preconditioner.schur_complement_two(op, lambda op: op.even_odd_sites_decomposed(parity)),
+                op.kappa(),
+            )
+        )
+
+    return instantiate

@@ -169,6 +169,10 @@ int cgptb_apply_fermion_operator(cgptb_fermion_operator* op, int opcode, const c
    import -> apply -> export.  Synchronous.                                                               */
 int cgptb_apply_fermion_operator_host(cgptb_fermion_operator* op, int opcode, const void* src_host, void* dst_host, size_t nbytes);
 
+/* gpt.scale_per_coordinate(d, s, a, dim) (lib/gpt/core/transform.py:210-214, cgpt.lattice_scale_per_coordinate): d = a[x_dim] s,
+   a = n complex factors (re,im), dim counts the fifth dimension as 0 on 5d lattices */
+int cgptb_lattice_scale_per_coordinate(cgptb_lattice* d, const cgptb_lattice* s, const double* a_re_im, int n, int dim);
+
 /* ---- random numbers: cgpt.create_random(engine, seed) / cgpt.random_sample(rng, params) / cgpt.delete_random
    (lib/cgpt/lib/random.cc:38-101, random/engine.h:64-125).  Same streams as the reference: RANLUX24 lanes seeded by
    SHA-256, one generator per 2^4 block of sites, values drawn in double.  engine: "vectorized_ranlux24_389_64" (default

@@ -696,3 +696,17 @@ def test_zmobius(g, precision):
         x = g(slv * src5)
         r = g(m * x - src5)
         assert (g.norm2(r) / g.norm2(src5)) ** 0.5 < 1e-6
+        # the production preconditioner of zMoebius runs (applications/propagator/rbc/24D.py:16-61): kappa-rescaled Schur complement
+        kap = m.kappa()
+        half = to_spinor(g, m.F_grid_eo, s5, g.odd)
+        back = g(kap.inv() * kap * half)
+        assert (g.norm2(g(back - half)) / g.norm2(half)) ** 0.5 < 1e-14
+        ks = 1.0 / (2.0 * (mo.bs * (4.0 - 1.8) + 1.0))
+        ref = e.proj(s5, 1) * ks.reshape(-1, 1, 1)
+        assert rel(from_spinor(g(kap * half), s5), ref) < 1e-14
+        cg2 = inv.cg(eps=1e-8, maxiter=2000)
+        slv2 = inv.preconditioned(g.qcd.fermion.preconditioner.eo2_kappa_ne(), cg2)(m)
+        x2 = g(slv2 * src5)
+        r = g(m * x2 - src5)
+        assert (g.norm2(r) / g.norm2(src5)) ** 0.5 < 1e-6
+        assert rel(x2[:], x[:]) < 1e-6
