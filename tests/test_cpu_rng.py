@@ -81,3 +81,33 @@ def test_product_rng_grid_objects_and_errors():
         g.grid([3, 4, 4, 4], g.double)  # odd extent: neither checkerboards nor 2^4 rng blocks
     with pytest.raises(KeyError):
         rng.normal(None, {"sigmaa": 1.0})
+
+
+@pytest.mark.parametrize("mpi", [[1, 1, 1, 2], [1, 1, 2, 2], [1, 2, 1, 1]])
+def test_product_rng_is_decomposition_independent(mpi):
+    """every rank draws the blocks of its part of the global lattice (block seeds carry the global block index,
+    lib/cgpt/lib/random/parallel.h:74-89): stitched together, the ranks' fields are the single-rank field"""
+    from gpt_b200 import cgpt
+
+    gd = [4, 4, 4, 8]
+    p = {"distribution": "cnormal", "mu": 0.0, "sigma": 1.0}
+    for five_d in (False, True):
+        g_dims = ([3] if five_d else []) + gd
+        m = ([1] if five_d else []) + mpi
+        rng = g.random("decomposition")
+        ref = cgpt.random_sample_host(rng.obj, 1, g_dims, g_dims, [0] * len(g_dims), 12, p).reshape(g_dims[::-1] + [12])
+        ld = [d // k for d, k in zip(g_dims, m)]
+        out = np.zeros_like(ref)
+        key = 100
+        for rank in range(int(np.prod(m))):
+            co, r = [], rank
+            for k in m:
+                co.append(r % k)
+                r //= k
+            ls = [c * n for c, n in zip(co, ld)]
+            rr = g.random("decomposition")  # a fresh engine per rank, like one process per GPU
+            key += 1
+            loc = cgpt.random_sample_host(rr.obj, key, ld, g_dims, ls, 12, p).reshape(ld[::-1] + [12])
+            sl = tuple(slice(s, s + n) for s, n in zip(ls[::-1], ld[::-1]))
+            out[sl] = loc
+        assert np.array_equal(out, ref)
