@@ -9,9 +9,8 @@
 //     of TRL time slices); a persistent CTA (one per SM) walks its items and sweeps each along t;
 //   * per time slice the producer loads, for each of the three 32-byte component planes, the centre box of the tile
 //     (64 sites, as bottom / middle / top z layers) and its six (x/2, y, z) faces (16 sites each) -- 27 box loads with the
-//     128-byte swizzle, each shared
-//     memory row being the 4 x 32 B of one site -- plus the tile's 64 x 8 links (two boxes of four links each):
-//     2.5 spinor loads per output site instead of 8, all address arithmetic done by the TMA unit;
+//     128-byte swizzle, each shared memory row being the 4 x 32 B of one site -- plus the tile's 64 x 8 links (two boxes
+//     of four links each): 2.5 spinor loads per output site instead of 8, all address arithmetic done by the TMA unit;
 //   * only two stages (2 x 98 KB) fit into shared memory, so each stage is handed back in two halves (after the fourth
 //     and after the last hop of a step) and refilled in two halves: every byte is requested 1.5 steps ahead of its use;
 //   * the +-t neighbours never travel twice: the thread that owns (site, s) reads its own entry of the centre box once
