@@ -10,6 +10,7 @@ from gpt_b200.core import *  # noqa: F401,F403
 from gpt_b200.core import eval, slice, time, complex  # noqa: F401,A004  (GPT's names shadow builtins on purpose)
 from gpt_b200 import algorithms, qcd
 from gpt_b200.random import random  # noqa: F401
+from gpt_b200.gamma import gamma  # noqa: F401
 from gpt_b200.io import load, save, format  # noqa: F401,A004
 import sys as _sys
 

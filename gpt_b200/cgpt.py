@@ -55,6 +55,7 @@ SIGNATURES = {
     "cgptb_comm_finalize": (c_int, []),
     "cgptb_comm_info": (c_int, [_pi, _pi, _pi, _pi]),
     "cgptb_comm_globalsum": (c_int, [_pd, c_int]),
+    "cgptb_lattice_spin_matrix": (c_int, [c_void_p, c_void_p, _pd]),
     "cgptb_lattice_scale_per_coordinate": (c_int, [c_void_p, c_void_p, _pd, c_int, c_int]),
     "cgptb_lattice_pack_rhs": (c_int, [c_void_p, ctypes.POINTER(c_void_p), c_int, c_int]),
     "cgptb_gauge_plaquette": (c_int, [ctypes.POINTER(c_void_p), _pd]),
@@ -457,6 +458,13 @@ def random_sample(h, grid_key, lattice, p):
 def random_su3_links(h, grid_key, U, scale):
     arr = (c_void_p * 4)(*U)
     _check(_lib_ready().cgptb_random_su3_links(c_void_p(h), int(grid_key), arr, float(scale)))
+
+
+def lattice_spin_matrix(d, s, m):
+    import numpy as np
+
+    m = np.ascontiguousarray(np.asarray(m, dtype=np.complex128).reshape(4, 4))
+    _check(_lib_ready().cgptb_lattice_spin_matrix(c_void_p(d), c_void_p(s), m.view(np.float64).ctypes.data_as(_pd)))
 
 
 def lattice_scale_per_coordinate(d, s, a, dim):

@@ -370,11 +370,61 @@ __global__ void k_scale_per_coordinate(Geom g, int cb, int ls, int nd, int dim, 
   dst[o + 1] = ar * im + ai * re;
 }
 
+
+// dst = G src for a constant 4 x 4 complex spin matrix G (gamma matrices, chiral projectors, sigma_{mu nu}: g.gamma[...] * field,
+// lib/gpt/core/gamma.py:28-80); one thread per site, zero entries of G are skipped (uniform branch)
+struct SpinMatrix {
+  double re[16], im[16];
+};
+template <typename T>
+__global__ void __launch_bounds__(128) k_spin_matrix(size_t n, const T* __restrict__ in, T* __restrict__ out, SpinMatrix G) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  T psi[24], r[24];
+  load_spinor(in, n, i, psi);
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      T re = 0, im = 0;
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const T gr = (T)G.re[4 * a + b], gi = (T)G.im[4 * a + b];
+        if (gr == 0 && gi == 0) continue;
+        re += gr * psi[(3 * b + c) * 2] - gi * psi[(3 * b + c) * 2 + 1];
+        im += gr * psi[(3 * b + c) * 2 + 1] + gi * psi[(3 * b + c) * 2];
+      }
+      r[(3 * a + c) * 2] = re;
+      r[(3 * a + c) * 2 + 1] = im;
+    }
+  }
+  store_spinor(out, n, i, r);
+}
+
 }  // namespace cgptb
 
 using namespace cgptb;
 
 extern "C" {
+
+int cgptb_lattice_spin_matrix(cgptb_lattice* d, const cgptb_lattice* s, const double* m_re_im) {
+  CGPTB_API_BEGIN
+  CGPTB_ASSERT(d && s && m_re_im && same_shape(d, s) && d->data != s->data);
+  if (s->otype != CGPTB_OT_VSPINCOLOR) CGPTB_ERR("spin matrices act on spin-colour vector fields");
+  d->cb = s->cb;
+  SpinMatrix G;
+  for (int k = 0; k < 16; k++) {
+    G.re[k] = m_re_im[2 * k];
+    G.im[k] = m_re_im[2 * k + 1];
+  }
+  const unsigned blocks = (unsigned)((s->sites + 127) / 128);
+  if (s->prec == CGPTB_SINGLE)
+    k_spin_matrix<float><<<blocks, 128, 0, g_stream>>>(s->sites, (const float*)s->data, (float*)d->data, G);
+  else
+    k_spin_matrix<double><<<blocks, 128, 0, g_stream>>>(s->sites, (const double*)s->data, (double*)d->data, G);
+  LAUNCH_CHECK();
+  CGPTB_API_END
+}
 
 int cgptb_lattice_scale_per_coordinate(cgptb_lattice* d, const cgptb_lattice* s, const double* a_re_im, int n, int dim) {
   CGPTB_API_BEGIN

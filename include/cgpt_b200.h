@@ -169,6 +169,8 @@ int cgptb_apply_fermion_operator(cgptb_fermion_operator* op, int opcode, const c
    import -> apply -> export.  Synchronous.                                                               */
 int cgptb_apply_fermion_operator_host(cgptb_fermion_operator* op, int opcode, const void* src_host, void* dst_host, size_t nbytes);
 
+/* d = G s for a constant 4 x 4 complex spin matrix G (row-major, (re,im)): g.gamma[...] * field (lib/gpt/core/gamma.py:28-80) */
+int cgptb_lattice_spin_matrix(cgptb_lattice* d, const cgptb_lattice* s, const double* m_re_im);
 /* gpt.scale_per_coordinate(d, s, a, dim) (lib/gpt/core/transform.py:210-214, cgpt.lattice_scale_per_coordinate): d = a[x_dim] s,
    a = n complex factors (re,im), dim counts the fifth dimension as 0 on 5d lattices */
 int cgptb_lattice_scale_per_coordinate(cgptb_lattice* d, const cgptb_lattice* s, const double* a_re_im, int n, int dim);

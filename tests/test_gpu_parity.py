@@ -710,3 +710,39 @@ def test_zmobius(g, precision):
         r = g(m * x2 - src5)
         assert (g.norm2(r) / g.norm2(src5)) ** 0.5 < 1e-6
         assert rel(x2[:], x[:]) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------------
+# g.gamma: spin matrices on fields; gamma_5 hermiticity and the twisted-mass identity of the reference's test
+# (tests/qcd/fermion_operators.py:80-95)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["double", "single"])
+def test_gamma_algebra_on_fields(g, fields, precision):
+    grid, w, wo = _ops4(g, fields, CLOVER, precision)
+    tol = TOL[precision]
+    cdt = grid.precision.complex_dtype
+    s_np = fields["srcw"].astype(cdt)
+    src = to_spinor(g, grid, s_np)
+    for key in [0, 1, 2, 3, 5, "I", (0, 1), (2, 3)]:
+        mat = qcd.gamma[key] if not isinstance(key, tuple) else qcd.sigma(*key)
+        got = from_spinor(g(g.gamma[key] * src), s_np)
+        assert rel(got, qcd.spin_mul(mat.astype(cdt), s_np)) < tol, key
+    Pp, Pm = 0.5 * (g.gamma["I"] + g.gamma[5]), 0.5 * (g.gamma["I"] - g.gamma[5])
+    assert rel(from_spinor(g(Pp * src + Pm * src), s_np), s_np) < tol
+    assert rel(from_spinor(g(Pp * Pm * src), s_np) + s_np, s_np) < tol  # P+ P- = 0
+    # gamma_5 hermiticity of the Wilson-clover operator: g5 M g5 = M^dag
+    a = g(g.gamma[5] * w * g.gamma[5] * src)
+    b = g(w.adj() * src)
+    assert (g.norm2(g(a - b)) / g.norm2(b)) ** 0.5 < tol
+    # twisted mass: M_tm = M_wilson + i mu gamma_5
+    grid, wt, _ = _ops4(g, fields, dict(mass=-1.8, mu=0.3, boundary_phases=[1.0, 1.0, 1.0, -1.0]), precision)
+    grid, w0, _ = _ops4(g, fields, dict(mass=-1.8, csw_r=0.0, csw_t=0.0, xi_0=1.0, nu=1.0, isAnisotropic=False,
+                                        boundary_phases=[1.0, 1.0, 1.0, -1.0]), precision)
+    lhs = g(w0 * src + 0.3j * (g.gamma[5] * src))
+    rhs = g(wt * src)
+    assert (g.norm2(g(lhs - rhs)) / g.norm2(rhs)) ** 0.5 < tol
+    # 5d fields too
+    grid5, m, mo = _ops5(g, fields, MOBIUS, precision)
+    s5 = fields["src5"].astype(cdt)
+    got = from_spinor(g(g.gamma[5] * to_spinor(g, m.F_grid, s5)), s5)
+    assert rel(got, qcd.spin_mul(qcd.gamma[5].astype(cdt), s5)) < tol
