@@ -577,6 +577,35 @@ def inner_product_norm2(a, b):
     return a.grid.globalsum(ip), a.grid.globalsum(n2)
 
 
+def separate(x, dimension=0):
+    """5d field(s) -> list of the 4d fields of the slices of dimension 0 (gpt.separate, lib/gpt/core/transform.py; device copies)"""
+    assert dimension == 0
+    if isinstance(x, list):
+        return [y for f in x for y in separate(f, dimension)]
+    if isinstance(x, expr):
+        x = eval(x)
+    grid4 = x.grid.removed_dimension(0)
+    out = [lattice(grid4, x.otype) for _ in range(x.grid.fdimensions[0])]
+    cgpt.lattice_pack_rhs(x.obj, [o.obj for o in out], unpack=True)
+    return out
+
+
+def merge(lst, dimension=0, N=-1):
+    """list of 4d fields -> 5d field(s) with N slices each (all of them for N = -1); gpt.merge"""
+    assert dimension == 0
+    lst = [eval(y) if isinstance(y, expr) else y for y in lst]
+    if N == -1:
+        N = len(lst)
+    assert len(lst) % N == 0
+    out = []
+    for i in range(0, len(lst), N):
+        grid5 = lst[i].grid.inserted_dimension(0, N)
+        l5 = lattice(grid5, lst[i].otype)
+        cgpt.lattice_pack_rhs(l5.obj, [y.obj for y in lst[i:i + N]])
+        out.append(l5)
+    return out[0] if len(out) == 1 else out
+
+
 def scale_per_coordinate(d, s, a, dim):
     """d = a[x_dim] * s (lib/gpt/core/transform.py:210-214)"""
     if isinstance(s, expr):

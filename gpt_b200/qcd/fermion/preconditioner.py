@@ -1,6 +1,7 @@
 """even-odd preconditioners (lib/gpt/qcd/fermion/preconditioner/even_odd_sites.py:23-72)"""
 import gpt_b200 as g
 from gpt_b200.params import params_convention
+from gpt_b200.qcd.fermion.mixed_dwf import mixed_dwf  # noqa: F401
 
 
 @params_convention(parity=None)

@@ -746,3 +746,32 @@ def test_gamma_algebra_on_fields(g, fields, precision):
     s5 = fields["src5"].astype(cdt)
     got = from_spinor(g(g.gamma[5] * to_spinor(g, m.F_grid, s5)), s5)
     assert rel(got, qcd.spin_mul(qcd.gamma[5].astype(cdt), s5)) < tol
+
+
+def test_madwf(g):
+    """MADWF (tests/qcd/domain_wall.py:140-164): Moebius Ls = 12 propagator through the zMoebius Ls = 10 inner operator; the
+    approximation is close to the direct solve and, wrapped into defect correction, converges to it"""
+    small = [4, 4, 4, 8]
+    grid = g.grid(small, g.double)
+    rng = g.random("madwf")
+    U = g.qcd.gauge.random(grid, rng, scale=0.3)
+    bc = [1.0, 1.0, 1.0, 1.0]
+    qm = g.qcd.fermion.mobius(U, dict(mass=0.08, M5=1.8, b=1.5, c=0.5, Ls=12, boundary_phases=bc))
+    qz = g.qcd.fermion.zmobius(U, dict(ZMOBIUS, boundary_phases=bc))
+    inv = g.algorithms.inverter
+    pc = g.qcd.fermion.preconditioner
+    slv_5d = inv.preconditioned(pc.eo2_ne(), inv.cg(eps=1e-7, maxiter=2000))
+    slv_e = inv.preconditioned(pc.eo2_ne(), inv.cg(eps=1e-10, maxiter=2000))
+    src = rng.cnormal(g.vspincolor(grid))
+    direct = g(qm.propagator(slv_e) * src)
+    madwf = g(qm.propagator(pc.mixed_dwf(slv_5d, slv_5d, qz)) * src)
+    eps2 = g.norm2(g(madwf - direct)) / g.norm2(direct)
+    assert eps2 < 5e-3, eps2
+    madwf_dc = g(qm.propagator(inv.defect_correcting(pc.mixed_dwf(slv_5d, slv_5d, qz), eps=1e-8, maxiter=20)) * src)
+    eps2 = g.norm2(g(madwf_dc - direct)) / g.norm2(direct)
+    assert eps2 < 1e-12, eps2
+    # separate / merge round trip
+    x5 = rng.cnormal(g.vspincolor(qm.F_grid))
+    parts = g.separate(x5)
+    assert len(parts) == 12
+    assert g.norm2(g(g.merge(parts) - x5)) == 0.0
