@@ -775,3 +775,25 @@ def test_madwf(g):
     parts = g.separate(x5)
     assert len(parts) == 12
     assert g.norm2(g(g.merge(parts) - x5)) == 0.0
+
+
+def test_mobius_correlator_golden_from_seed(g):
+    """seed string in, physics out, no oracle in between: the reference's domain-wall test (tests/qcd/domain_wall.py:14-20,26-35,
+    116-137,252-283) through the drop-in API -- g.random("test") -> gauge.random(scale=2) on 8^4 in double, converted to single,
+    Moebius Ls = 12, point source at [0,1,0,0], eo2_ne CG (eps 1e-8, maxiter 1000), pion correlator against the 8 golden values"""
+    correlator_ref = [0.5534145832061768, 0.2355920523405075, 0.08622127771377563, 0.05764763802289963, 0.05238068848848343,
+                      0.057377591729164124, 0.08141942322254181, 0.21931196749210358]
+    rng = g.random("test")
+    U = g.qcd.gauge.random(g.grid([8, 8, 8, 8], g.double), rng, scale=2.0)
+    U = g.convert(U, g.single)
+    grid = U[0].grid
+    qm = g.qcd.fermion.mobius(U, dict(mass=0.08, M5=1.8, b=1.5, c=0.5, Ls=12, boundary_phases=[1.0, 1.0, 1.0, 1.0]))
+    src = g.mspincolor(grid)
+    g.create.point(src, [0, 1, 0, 0])
+    inv = g.algorithms.inverter
+    pc = g.qcd.fermion.preconditioner
+    cg_e = inv.cg({"eps": 1e-8, "maxiter": 1000})
+    dst = g(qm.propagator(inv.preconditioned(pc.eo2_ne(), cg_e)) * src)
+    correlator = g.slice(g.trace(dst * g.adj(dst)), 3)
+    eps = sum((correlator[t].real - correlator_ref[t]) ** 2.0 for t in range(8)) ** 0.5 / 8
+    assert eps < 1e-5, (eps, [c.real for c in correlator])
