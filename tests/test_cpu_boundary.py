@@ -115,3 +115,54 @@ def test_nersc_header_parsing(tmp_path):
     assert nersc.read_header(str(tmp_path / "missing")) is None
     assert nersc._tolerance("0.588123", 1e-16) == 1e-4 and nersc._tolerance("1.5e-3", 1e-7) == 10.0
     assert nersc.format.nersc(label="x").params == {"label": "x", "id": "gpt", "sequence_number": 1}
+
+
+def test_gamma_algebra_host():
+    """g.gamma tables and their algebra (numpy side; the kernel is covered by the GPU tests): Clifford algebra, hermiticity,
+    gamma_5 = gamma_0 gamma_1 gamma_2 gamma_3, sigma_{mu nu} against the oracle's basis (lib/gpt/core/gamma.py:28-53)"""
+    import numpy as np
+
+    import gpt_b200 as g
+    from oracle import qcd
+
+    for mu in range(4):
+        assert np.array_equal(g.gamma[mu].matrix, qcd.gamma[mu])
+        assert np.array_equal(g.gamma["XYZT"[mu]].matrix, qcd.gamma[mu])
+        assert np.allclose(g.gamma[mu].adj().matrix, g.gamma[mu].matrix)
+        for nu in range(4):
+            acomm = (g.gamma[mu] * g.gamma[nu] + g.gamma[nu] * g.gamma[mu]).matrix
+            assert np.allclose(acomm, 2.0 * np.identity(4) * (mu == nu))
+            if mu != nu:
+                assert np.allclose(g.gamma[mu, nu].matrix, qcd.sigma(mu, nu))
+    g5 = g.gamma[0] * g.gamma[1] * g.gamma[2] * g.gamma[3]
+    assert np.allclose(g5.matrix, g.gamma[5].matrix)
+    Pp, Pm = 0.5 * (g.gamma["I"] + g.gamma[5]), 0.5 * (g.gamma["I"] - g.gamma[5])
+    assert np.allclose((Pp * Pp).matrix, Pp.matrix) and np.allclose((Pp * Pm).matrix, 0.0) and np.allclose((Pp + Pm).matrix, np.identity(4))
+    assert np.allclose((g.gamma[5].inv() * g.gamma[5]).matrix, np.identity(4))
+    assert np.allclose((-g.gamma[2]).matrix, -qcd.gamma[2]) and np.allclose((2j * g.gamma[2]).matrix, 2j * qcd.gamma[2])
+
+
+def test_params_convention_semantics():
+    """same calling conventions as lib/gpt/params.py:20-82: dict and keyword arguments merge, positional arguments with defaults
+    may be omitted, unknown parameters raise"""
+    import pytest
+
+    from gpt_b200.params import params_convention
+
+    @params_convention(a=1, b=2)
+    def f(x, y=None, p={}):
+        return x, y, p
+
+    assert f(5) == (5, None, {"a": 1, "b": 2})
+    assert f(5, 6, {"a": 3}) == (5, 6, {"a": 3, "b": 2})
+    assert f(5, 6, {"a": 3}, b=4) == (5, 6, {"a": 3, "b": 4})
+    assert f(5, b=7) == (5, None, {"a": 1, "b": 7})
+    with pytest.raises(KeyError):
+        f(5, c=1)
+
+    class C:
+        @params_convention(eps=1e-15)
+        def __init__(self, params):
+            self.params = params
+
+    assert C().params == {"eps": 1e-15} and C(eps=1e-8).params == {"eps": 1e-8} and C({"eps": 1e-3}).params == {"eps": 1e-3}
