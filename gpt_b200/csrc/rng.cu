@@ -14,6 +14,8 @@
 //   gauge.random: su(3) generators, A = scale sum_a u_a T_a, exp(iA)      lib/gpt/qcd/gauge/create.py:66-71,
 //       lib/gpt/core/object_type/su_n.py:208-240, lib/gpt/core/foundation/lattice/matrix/exp.py:167-219
 #include <math.h>
+#include <omp.h>
+#include <stdlib.h>
 #include <stdint.h>
 #include <string.h>
 #include <complex>
@@ -424,6 +426,16 @@ int cgptb_create_random(cgptb_random** out, const char* engine, const char* seed
     luxury = 24;
   else
     CGPTB_ERR("Unknown rng engine type: %s", engine);
+  // torchrun exports OMP_NUM_THREADS=1 to every rank; the generators are host code, so give each rank its share of the cores
+  // (one process per GPU: cores / LOCAL_WORLD_SIZE) unless the user asked for more than one thread explicitly
+  {
+    const char* lws = getenv("LOCAL_WORLD_SIZE");
+    const char* ont = getenv("OMP_NUM_THREADS");
+    if (lws && atoi(lws) >= 1 && (!ont || atoi(ont) <= 1)) {
+      int share = omp_get_num_procs() / atoi(lws);
+      if (share > omp_get_max_threads()) omp_set_num_threads(share);
+    }
+  }
   cgptb_random* r = new cgptb_random;
   r->seed = seed;
   r->luxury = luxury;
