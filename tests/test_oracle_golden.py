@@ -200,3 +200,24 @@ def test_wilson_pion_correlator_golden():
         sol, hist = qcd.propagator_column(w, src, 1e-6, 1000)
         corr += np.sum(np.abs(sol) ** 2, axis=(1, 2, 3, 4, 5))
     assert np.linalg.norm(corr - np.array(PION_REF)) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+@pytest.mark.parametrize("Ls", [12, 8, 5])
+def test_c_port_matches_numpy_oracle(dtype, Ls):
+    """oracle/dslash_ref.c (bench.py's CPU baseline) against the numpy restatement of the reference's hopping term, both
+    directions of the dagger, anisotropic coefficients"""
+    from oracle import cref
+
+    dims = [4, 6, 4, 8]
+    rng = random("c port")
+    U = qcd.gauge_random(rng, dims, scale=0.9)
+    V = qcd.apply_boundary_phases(U, [1.0, -1.0, np.exp(0.3j), -1.0])
+    psi = rng.cnormal([Ls] + dims, (4, 3)).astype(dtype)
+    Vc = np.stack([v.reshape(-1, 3, 3) for v in V]).astype(dtype)
+    coef = (1.3, 1.3, 1.3, 1.0)
+    tol = 1e-14 if dtype == np.complex128 else 2e-6
+    for dag in (False, True):
+        ref = qcd.dhop([v.astype(dtype) for v in V], psi, coef, dag, five_d=True)
+        a = cref.dhop(dims, Ls, Vc, psi.reshape(-1, 4, 3), coef, dag).reshape(ref.shape)
+        assert np.linalg.norm(a - ref) / np.linalg.norm(ref) < tol
