@@ -221,3 +221,44 @@ def test_c_port_matches_numpy_oracle(dtype, Ls):
         ref = qcd.dhop([v.astype(dtype) for v in V], psi, coef, dag, five_d=True)
         a = cref.dhop(dims, Ls, Vc, psi.reshape(-1, 4, 3), coef, dag).reshape(ref.shape)
         assert np.linalg.norm(a - ref) / np.linalg.norm(ref) < tol
+
+
+def test_fixture_matches_embedded_numbers():
+    """tests/golden/reference_vectors.json (made by tests/golden/extract_reference_vectors.py from the reference's own tests)
+    holds exactly the numbers the parity tests assert; where the reference tree is available the extraction is repeated"""
+    import importlib.util
+    import json
+    import os
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, "golden", "reference_vectors.json")) as f:
+        gold = json.load(f)
+    fp = gold["fingerprints"]
+
+    def c(entry, key):
+        re_, im_ = entry["values"][key]
+        return complex(re_, im_)
+
+    assert c(fp["wilson_matrices"], "") == -999.7564252326631 - 466.7758727463097j
+    assert c(fp["wilson_clover_matrices"], ".Mdiag") == -908.620454398646 - 3428.779878527792j
+    assert c(fp["wilson_clover_matrices_open"], "") == -1634.2615676797234 + 239.27037187495998j
+    assert c(fp["wilson_twisted_mass_matrices"], ".Mdiag") == -440.5312395819657 - 1102.362512575698j
+    assert c(fp["mobius_matrices"], "") == -8693.09425573421 - 4130.7793316734915j
+    assert c(fp["mobius_axial_mass_matrices"], ".ImportPhysicalFermionSource") == -97.93443075274081 - 690.6405168964941j
+    assert c(fp["zmobius_matrices"], "") == -2424.048033434305 + 10557.661684178218j
+    assert c(fp["zmobius_matrices"], ".ImportPhysicalFermionSource") == 4064.7879718582053 - 1357.0856808000196j
+    assert fp["wilson_clover_params"]["values"] == {k: (list(v) if isinstance(v, (list, tuple)) else v) for k, v in CLOVER.items()}
+    assert gold["wilson_pion_correlator"]["values"] == list(PION_REF)
+    assert gold["domain_wall_correlator_ref"]["values"][0] == 0.5534145832061768
+    assert gold["rng_normal_sequences"][0]["values"] == [-0.29101665386129116, -1.4591269443435488, -0.3641310411719848,
+                                                         -0.9454532383815435, 0.4996115272362977]
+    assert gold["rng_normal_sequences"][1]["values"][0] == 1.473846437649123
+    assert [r["plaquette"] for r in gold["rng_gauge_random_plaquettes"]["values"]] == [-0.00014108397456619623, -0.00014108397456619623,
+                                                                                        0.38723058417632267]
+    assert gold["rng_choice_letters"]["values"] == ["C", "C", "A", "C", "C", "B", "A", "B", "C", "A"]
+    assert gold["rng_choice_numbers"]["values"] == [2, 3, 3, 3, 1]
+    if os.path.isdir("/root/reference/tests"):
+        spec = importlib.util.spec_from_file_location("extract_reference_vectors", os.path.join(here, "golden", "extract_reference_vectors.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        assert json.loads(json.dumps(mod.extract("/root/reference"), sort_keys=True)) == gold
