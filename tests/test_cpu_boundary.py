@@ -166,3 +166,22 @@ def test_params_convention_semantics():
             self.params = params
 
     assert C().params == {"eps": 1e-15} and C(eps=1e-8).params == {"eps": 1e-8} and C({"eps": 1e-3}).params == {"eps": 1e-3}
+
+
+def test_bench_reference_arm_prints_contract_line():
+    """`python bench.py --impl reference` needs no GPU: one JSON line with the keys of the bench contract (impl, metric, unit, value,
+    cpu_baseline kind / cores / sample, e2e with zero copy bytes)"""
+    import json
+    import subprocess
+    import sys
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "mobius_dwf_dslash_gflops" and d["unit"] == "GFlop/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["steps"] == 2 and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "Dhop" in d["cpu_baseline"]["sample"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
