@@ -7,6 +7,21 @@ Moebius domain-wall `Dhop` (opcode 3001, the loop of /root/reference/benchmarks/
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
 
 One "step" = one application of Dhop to the full 5d field.  Prints ONE JSON line (rank 0).
+
+What the line holds (native arm):
+  value / ms_per_step   K steps timed on the device AFTER the loop has already run for >= --preheat seconds, i.e. with
+                        sw_power_cap engaged (the sustained number); `first_window` is the same K steps timed right after
+                        the W warm-up steps of a cold GPU (what a short run would have reported)
+  parity                the result of the timed operator on THIS lattice (every rank's block of the split lattice, halo slices
+                        included) against oracle/dslash_ref.c on >= 1e5 sampled 5d sites; the run fails above 1e-5
+  roofline              compulsory bytes of the even-odd kernel / measured launch time / measured HBM peak
+  e2e                   the same Dhop through the host-buffer call (upload, stencil, download inside the timed region)
+  e2e_solve             a propagator column: 4d host source -> upload -> eo2_ne CG -> 4d solution -> download
+  eo_cg                 fused device CG: ms per iteration; time_to_solve: defect_correcting(mixed_precision(eo2_ne CG)) to 1e-8
+                        with the true residual, and the same solver stack on a small lattice next to the CPU oracle
+  kernels               GB/s of the CG's vector kernels and s-direction operators on the half lattice
+  cpu_baseline          oracle/dslash_ref.c (OpenMP, all host cores) on the same lattice, a bounded number of applications
+
 Flop / byte accounting: SURVEY.md 8(d) -- 1320 flop per 5d site; compulsory bytes per output site of the
 even-odd kernel = (24 in + 24 out + 144/Ls links) reals; GPT's "effective" bytes (benchmarks/dslash.py:55-62)
 are reported next to it.
@@ -28,6 +43,7 @@ DIMS = [32, 32, 32, 64]
 LS = 12
 FLOPS_PER_SITE = 1320  # 8*Nc*(7+16*Nc), benchmarks/dslash.py:53
 MOBIUS = dict(mass=0.08, M5=1.8, b=1.5, c=0.5, Ls=LS, boundary_phases=[1.0, 1.0, 1.0, 1.0])  # benchmarks/dslash.py:30-40
+WORKLOAD = "Mobius DWF Dhop 32^3x64 Ls=12 single per GPU (BASELINE.json configs[2]; T-split, global T=64*n_gpus)"
 
 
 def peaks():
@@ -62,13 +78,10 @@ class clock_sampler:
         for line in self.proc.stdout:
             self.lines.append((time.time(), line.strip()))
 
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for ts, line in self.lines:
-            if ts < t0 or ts > t1 + 0.2:
+    def window(self, t0, t1):
+        sm, mx, pw, reasons = [], [], [], set()
+        for ts, line in list(self.lines):
+            if ts < t0 or ts > t1:
                 continue
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
@@ -76,13 +89,44 @@ class clock_sampler:
             try:
                 sm.append(float(f[1]))
                 mx.append(float(f[2]))
+                pw.append(float(f[3]))
             except ValueError:
                 continue
             for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w": float(np.median(pw)) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+
+def numa_bind(local_rank):
+    """run this rank (and therefore its pinned host buffers: first touch) on the NUMA node of its GPU"""
+    try:
+        import torch
+
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        with open(path) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
 
 
 def gell_mann_half():
@@ -100,27 +144,67 @@ def gell_mann_half():
     return lam / 2
 
 
-def synthetic_fields_device(torch, dims, ls, seed):
-    """links = exp(i * 0.5 * sum_a u_a T_a), u_a ~ U[-1/2,1/2); source = N(0,1) + i N(0,1)   (SURVEY 8(d)),
-    generated on the device with torch's RNG (the reference's RANLUX stream is only needed for parity tests)."""
-    gen = torch.Generator(device="cuda")
-    gen.manual_seed(seed)
-    v4 = int(np.prod(dims))
-    T = torch.tensor(gell_mann_half(), dtype=torch.complex64, device="cuda")
-    U = []
+# ---- parity of the timed operator on the bench lattice ------------------------------------------------------------------
+def parity_check(torch, dist, cgpt, U, src, dst, dims, world, rank, n_sites4=9000):
+    """
+    Compare dst = Dhop src (already computed on the device) with oracle/dslash_ref.c on sampled sites of this rank's
+    block.  The block is padded with the last / first time slice of the T-neighbours (its own, periodically, for one
+    rank), so boundary sites check the halo exchange; a quarter of the sample lies on the two boundary slices.
+    Returns (rel_err, n_5d_sites); the caller takes the max over ranks.
+    """
+    from oracle import cref
+
+    cref.set_num_threads(max(1, cref.host_cores() // max(1, min(world, 8))))
+    X, Y, Z, T = dims
+    v3 = X * Y * Z
+    slice_c = v3 * LS * 12  # complex numbers per time slice of the 5d field
+    psi = np.empty((T + 2) * slice_c, dtype=np.complex64)
+    cgpt.lattice_export_ptr(src.obj, psi[slice_c:].ctypes.data, T * slice_c * 8)
+    V = np.empty((4, (T + 2) * v3 * 9), dtype=np.complex64)
     for mu in range(4):
-        u = torch.rand((v4, 8), generator=gen, device="cuda", dtype=torch.float32) - 0.5
-        A = torch.einsum("na,aij->nij", (0.5 * u).to(torch.complex64), T)
-        U.append(torch.linalg.matrix_exp(1j * A).contiguous())
-    src = torch.randn((v4 * ls, 4, 3, 2), generator=gen, device="cuda", dtype=torch.float32)
-    return U, torch.view_as_complex(src).contiguous()
+        cgpt.lattice_export_ptr(U[mu].obj, V[mu, v3 * 9:].ctypes.data, T * v3 * 9 * 8)
+
+    def neighbours(first, last):
+        """(last slice of the rank below, first slice of the rank above) of a per-rank pair of boundary slices"""
+        if world == 1:
+            return last, first
+        mine = torch.from_numpy(np.stack([first, last])).cuda()
+        every = torch.empty((world,) + tuple(mine.shape), dtype=mine.dtype, device="cuda")
+        dist.all_gather_into_tensor(every, mine)
+        lo, hi = (rank - 1) % world, (rank + 1) % world  # mpi = 1.1.1.N: the rank is the T coordinate
+        return every[lo, 1].cpu().numpy(), every[hi, 0].cpu().numpy()
+
+    lo, hi = neighbours(psi[slice_c:2 * slice_c].copy(), psi[T * slice_c:(T + 1) * slice_c].copy())
+    psi[:slice_c], psi[(T + 1) * slice_c:] = lo, hi
+    n = v3 * 9
+    lo, hi = neighbours(V[:, n:2 * n].copy(), V[:, T * n:(T + 1) * n].copy())
+    V[:, :n], V[:, (T + 1) * n:] = lo, hi
+
+    rs = np.random.default_rng(1234 + rank)
+    nb = n_sites4 // 8
+    t_of = np.concatenate([np.zeros(nb, np.int64), np.full(nb, T - 1, np.int64), rs.integers(0, T, n_sites4 - 2 * nb)])
+    idx_local = rs.integers(0, v3, n_sites4) + v3 * t_of
+    idx_local = np.unique(idx_local)
+    ref = cref.dhop_sites([X, Y, Z, T + 2], LS, V.reshape(4, -1, 3, 3), psi.reshape(-1, 4, 3), idx_local + v3)
+    del psi, V
+    out = np.empty(T * slice_c, dtype=np.complex64)
+    cgpt.lattice_export_ptr(dst.obj, out.ctypes.data, out.nbytes)
+    got = out.reshape(T * v3, LS * 12)[idx_local].reshape(-1)
+    ref = ref.reshape(-1)
+    err = float(np.linalg.norm(got.astype(np.complex128) - ref) / np.linalg.norm(ref.astype(np.complex128)))
+    return err, int(idx_local.size) * LS
+
+
+def allmax(torch, dist, x):
+    if dist is None:
+        return x
+    t = torch.tensor([x], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
 
 
 def run_native(args):
     import torch
-
-    import gpt_b200 as g
-    from gpt_b200 import cgpt
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -129,6 +213,11 @@ def run_native(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
     torch.cuda.set_device(local_rank)
+    numa_node = numa_bind(local_rank)
+
+    import gpt_b200 as g
+    from gpt_b200 import cgpt
+
     cgpt.init(local_rank)
     dist = None
     if world > 1:
@@ -164,42 +253,76 @@ def run_native(args):
         if dist is not None:
             dist.barrier()
 
+    def timed(fn, n):
+        """n calls of fn, device time on the library stream (CUDA events), max over ranks"""
+        sync()
+        cgpt.timer_start()
+        for _ in range(n):
+            fn()
+        ms = cgpt.timer_stop()
+        sync()
+        return allmax(torch, dist, ms)
+
+    def step():
+        qm.Dhop.mat(dst, src)
+
+    # ---- parity of exactly this operator / lattice / decomposition -------------------------------------------------
+    parity = None
+    if not args.no_parity:
+        step()
+        sync()
+        err, n5 = parity_check(torch, dist, cgpt, U, src, dst, dims, world, rank)
+        err = allmax(torch, dist, err)
+        parity = {"rel_err": err, "tolerance": 1e-5, "sites_checked_per_rank": n5, "ranks": world,
+                  "against": "oracle/dslash_ref.c on sampled sites of every rank's block (boundary slices included)",
+                  "lattice": gdims + [LS]}
+        if not err < 1e-5:
+            raise SystemExit(f"parity check failed: rel err {err} on {gdims} Ls={LS} ({world} ranks)")
+
+    # ---- the timed region ------------------------------------------------------------------------------------------
     sampler = clock_sampler(local_rank)
     for _ in range(args.warmup):
-        qm.Dhop.mat(dst, src)
-    sync()
-    time.sleep(1.0)  # let nvidia-smi start sampling
+        step()
     l0 = cgpt.launch_count()
-    t0 = time.time()
-    cgpt.timer_start()
-    for _ in range(args.steps):
-        qm.Dhop.mat(dst, src)
-    ms = cgpt.timer_stop()
-    sync()
-    t1 = time.time()
+    tw0 = time.time()
+    ms_first = timed(step, args.steps)  # a cold GPU: ends before the power cap engages if K is small
+    tw1 = time.time()
     launches = cgpt.launch_count() - l0
-    clocks = sampler.stop(t0, t1)
-    if dist is not None:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    # pre-heat: keep the same loop running until it has run for --preheat seconds, then time K steps again
+    n_pre = 0
+    t_pre = time.time()
+    while time.time() - t_pre < args.preheat:
+        for _ in range(50):
+            step()
+        cgpt.accelerator_barrier()
+        n_pre += 50
+    ts0 = time.time()
+    ms = timed(step, args.steps)
+    ts1 = time.time()
+    if ts1 - ts0 < 0.5:
+        time.sleep(0.3)  # let nvidia-smi (50 ms period) see the tail of the region
+    clocks = sampler.window(t_pre, ts1 + 0.1)
+    clocks_first = sampler.window(tw0, tw1 + 0.05)
+    sampler.stop()
     ms_per_step = ms / args.steps
     gflops = FLOPS_PER_SITE * v5 * world / (ms_per_step * 1e-3) / 1e9
 
-    # roofline of the dominant kernel k_dhop<float>: one launch per parity, two per step
+    # roofline of the dominant kernel: one launch per parity, two per step
     bytes_per_launch = (v5 // 2) * 48 * 4 + (v4 // 2) * 8 * 18 * 4
     launches_per_step = 2
     peak, peak_src = peaks()
     achieved = bytes_per_launch / (ms_per_step * 1e-3 / launches_per_step) / 1e9
     eff_bytes = (8 * 2 * 4 * 3 + 8 * 2 * 9 / LS + 2 * 4 * 3) * 4 * v5
-    traffic = None
+    traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "dhop_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            tj = json.load(f)
+        traffic = tj.get("dram_bytes_per_launch")
+        traffic_src = "not measured in this run: ncu --set full capture committed as " + tj.get("source", "profiles/dhop_traffic.json")
     except Exception:
         pass
 
-    # end to end through the public API with HOST buffers (pinned): import -> Dhop -> export
+    # ---- end to end through the public API with HOST buffers (pinned): import -> Dhop -> export ------------------------
     e2e = None
     if not args.no_e2e:
         nbytes = v5 * 12 * 8
@@ -211,21 +334,37 @@ def run_native(args):
         # with upload / stencil / download pipelined over slabs of time slices (gpt_b200/csrc/hostpipe.cu)
         for _ in range(2):
             qm.Dhop_host(h_out, h_in)
-        sync()
-        cgpt.timer_start()
-        for _ in range(n_e2e):
-            qm.Dhop_host(h_out, h_in)
-        ms_e = cgpt.timer_stop()
-        sync()
-        if dist is not None:
-            t = torch.tensor([ms_e], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_e = float(t.item())
+        ms_e = timed(lambda: qm.Dhop_host(h_out, h_in), n_e2e)
         e2e = {"value": FLOPS_PER_SITE * v5 * world / (ms_e / n_e2e * 1e-3) / 1e9, "unit": "GFlop/s",
-               "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": n_e2e, "ms_per_step": ms_e / n_e2e}
+               "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": n_e2e, "ms_per_step": ms_e / n_e2e,
+               "numa_node": numa_node,
+               "note": "one Dhop per upload+download: PCIe bound by construction; e2e_solve is the path as users run it"}
+        del h_in, h_out
 
-    # eo-CG time-to-solve (second half of BASELINE.json's metric): eo2_ne CG on the same operator and source,
-    # fixed iteration count so that the number is comparable across runs (single precision, device-side loop)
+    # ---- GB/s of the other kernels of the CG on the half lattice -------------------------------------------------------------
+    kernels = None
+    if not args.no_kernels:
+        a, b, c = (g.vspincolor(qm.F_grid_eo) for _ in range(3))
+        g.pick_checkerboard(g.odd, a, src)
+        g.pick_checkerboard(g.odd, b, dst)
+        c[:] = 0
+        reals = v5 // 2 * 4  # bytes per real per half-lattice site
+        table = [
+            ("axpy", lambda: g.axpy(c, 0.3, a, b), 72), ("inner_product", lambda: g.rank_inner_product(a, b), 48),
+            ("norm2", lambda: cgpt.lattice_norm2(a.obj), 24), ("psi_plus_a_p", lambda: cgpt.lattice_lc(c.obj, True, [0.3], [a.obj]), 72),
+            ("Mooee", lambda: qm.Mooee.mat(c, a), 48), ("MooeeInv", lambda: qm.Mooee.inv_mat(c, a), 48),
+            ("Meooe", lambda: qm.Meooe.mat(c, a), 60),
+        ]
+        kernels = {}
+        for name, fn, nreal in table:
+            for _ in range(3):
+                fn()
+            msk = timed(fn, 20) / 20
+            gbs = nreal * reals / (msk * 1e-3) / 1e9
+            kernels[name] = {"ms": msk, "GB/s": gbs, "frac_of_hbm_peak": gbs / peak, "reals_per_site": nreal}
+        del a, b, c
+
+    # ---- eo-CG (second half of BASELINE.json's metric) ------------------------------------------------------------------------------
     cg_info = None
     if not args.no_cg:
         half = g.vspincolor(qm.F_grid_eo)
@@ -243,33 +382,91 @@ def run_native(args):
             ms_try = cgpt.timer_stop()
             sync()
             ms_cg = ms_try if ms_cg is None else min(ms_cg, ms_try)
-        if dist is not None:
-            t = torch.tensor([ms_cg], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_cg = float(t.item())
+        ms_cg = allmax(torch, dist, ms_cg)
         cg_info = {"solver": "inv.preconditioned(pc.eo2_ne(), inv.cg) on Mpc^dag Mpc, fused device loop", "iterations": len(hist),
                    "ms_total": ms_cg, "ms_per_iteration": ms_cg / max(len(hist), 1),
                    "residual_reduction": (hist[-1] / hist[0]) ** 0.5 if hist else None,
                    "launches_per_iteration": (cgpt.launch_count() - l1) / max(len(hist), 1)}
         del half, psi
 
+    # ---- time to solve: wall time, iterations, true residual ----------------------------------------------------------
+    solve = None
+    e2e_solve = None
+    if not args.no_solve:
+        inv = g.algorithms.inverter
+        pc = g.qcd.fermion.preconditioner
+        # (a) a propagator column through the public API from a HOST source: upload once, solve, download once
+        src4 = g.vspincolor(qm.U_grid)
+        rng4 = g.random("bench_source", "vectorized_ranlux24_24_64")
+        rng4.cnormal(src4)
+        nb4 = v4 * 12 * 8
+        h_src = torch.empty(nb4, dtype=torch.uint8, pin_memory=True)
+        h_dst = torch.empty(nb4, dtype=torch.uint8, pin_memory=True)
+        cgpt.lattice_export_ptr(src4.obj, h_src.data_ptr(), nb4)
+        cg_sp = inv.cg(eps=args.solve_eps_single, maxiter=args.solve_maxiter)
+        prop = qm.propagator(inv.preconditioned(pc.eo2_ne(), cg_sp))
+        dst4 = g.vspincolor(qm.U_grid)
+        sync()
+        t0 = time.time()
+        cgpt.lattice_import_ptr(src4.obj, h_src.data_ptr(), nb4)
+        prop(dst4, src4)
+        cgpt.lattice_export_ptr(dst4.obj, h_dst.data_ptr(), nb4)
+        sync()
+        wall = allmax(torch, dist, time.time() - t0)
+        e2e_solve = {"what": "propagator column: 4d host source -> Import -> eo2_ne CG (single) -> Export -> 4d host solution",
+                     "seconds": wall, "iterations": len(cg_sp.history), "eps": args.solve_eps_single,
+                     "h2d_bytes": nb4, "d2h_bytes": nb4, "ms_per_iteration": wall * 1e3 / max(len(cg_sp.history), 1)}
+        del h_src, h_dst, prop
+        # (b) the production stack (tests/manual/mpi.py:104-110): double outer defect correction, single inner eo2_ne CG
+        qd = qm.converted(g.double)
+        src_d = g.convert(src4, g.double)
+        b5 = g(qd.ImportPhysicalFermionSource * src_d)
+        cg_in = inv.cg(eps=1e-4, maxiter=args.solve_maxiter)
+        dc = inv.defect_correcting(inv.mixed_precision(inv.preconditioned(pc.eo2_ne(), cg_in), g.single, g.double),
+                                   eps=args.solve_eps, maxiter=40)
+        x5 = g.lattice(b5)
+        x5[:] = 0
+        sync()
+        t0 = time.time()
+        dc(qd)(x5, b5)
+        sync()
+        wall = allmax(torch, dist, time.time() - t0)
+        r = g(qd * x5 - b5)
+        true_res = (g.norm2(r) / g.norm2(b5)) ** 0.5
+        solve = {"solver": "defect_correcting(mixed_precision(preconditioned(eo2_ne, cg(eps=1e-4)), single, double), eps=%g)" % args.solve_eps,
+                 "lattice": gdims + [LS], "seconds": wall, "outer_iterations": len(dc.history),
+                 "true_residual": float(true_res), "converged": bool(true_res < 10 * args.solve_eps)}
+        del qd, src_d, b5, x5, r, src4, dst4
+        # (c) the same stack on a lattice the numpy oracle finishes in seconds: GPU and CPU side by side
+        if rank == 0 and world == 1:
+            solve["small_lattice"] = small_solve_side_by_side(g)
+
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_baseline(sample_dims=[16, 16, 16, 32], seconds=12.0)
+    if rank == 0 and not args.no_cpu:
+        cpu = cpu_baseline(DIMS, seconds=args.cpu_seconds)
+    if dist is not None:
+        dist.barrier()
 
     if rank == 0:
         out = {
             "metric": "mobius_dwf_dslash_gflops", "value": gflops, "unit": "GFlop/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (g.random(\"benchmark\", ranlux24_24) links scale 0.5 + cnormal source, as benchmarks/dslash.py)",
-            "config": {"workload": "Mobius DWF Dhop 32^3x64 Ls=12 single per GPU (BASELINE.json configs[2]; T-split, global T=64*n_gpus)",
+            "config": {"workload": WORKLOAD,
                        "local_dims": dims, "Ls": LS, "cache": "inputs (2.4 GB field + 0.6 GB links) larger than L2, no flush needed",
-                       "global_dims": gdims, "parallelism": "mpi " + ".".join(str(m) for m in mpi) + " (x.y.z.t), halo exchange NCCL send/recv overlapped with the interior stencil"},
+                       "global_dims": gdims, "parallelism": "mpi " + ".".join(str(m) for m in mpi) + " (x.y.z.t), halo exchange overlapped with the interior stencil",
+                       "timing": f"K steps timed after {n_pre} untimed steps (>= {args.preheat} s of the same loop): sustained clocks; first_window = the K steps right after warm-up"},
+            "first_window": {"ms_per_step": ms_first / args.steps, "value": FLOPS_PER_SITE * v5 * world / (ms_first / args.steps * 1e-3) / 1e9,
+                             "clocks": clocks_first},
+            "parity": parity,
             "gbs_effective_gpt_convention": eff_bytes * world / (ms_per_step * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k_dhop_f32_tma (TMA-fed persistent t-sweep, packed FFMA2, one launch per parity)", "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": bytes_per_launch, "launches_per_step": launches_per_step},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "eo_cg": cg_info,
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": "k_dhop_f32_tma (TMA-fed persistent t-sweep, packed FFMA2, one launch per parity)", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_per_launch, "launches_per_step": launches_per_step,
+                         "frac_first_window": bytes_per_launch / (ms_first / args.steps * 1e-3 / launches_per_step) / 1e9 / peak},
+            "cpu_baseline": cpu, "e2e": e2e, "e2e_solve": e2e_solve, "gpu_launches": int(launches), "clocks": clocks,
+            "eo_cg": cg_info, "time_to_solve": solve, "kernels": kernels,
         }
         print(json.dumps(out))
     if dist is not None:
@@ -277,20 +474,56 @@ def run_native(args):
         dist.destroy_process_group()
 
 
+def small_solve_side_by_side(g):
+    """BASELINE.md 3.3 on a lattice the numpy oracle (oracle/qcd.py: cg.py restated) finishes in seconds: same operator,
+    source and eps on the GPU (double, through inv.preconditioned(eo2_ne, cg)) and on the CPU; iterations must agree"""
+    from oracle import qcd
+    from oracle.rng import random as oracle_random
+
+    dims, ls, eps = [8, 8, 8, 8], 8, 1e-8
+    rng = oracle_random("bench_small")
+    U = qcd.gauge_random(rng, dims, scale=0.5)
+    params = dict(mass=0.08, M5=1.8, b=1.5, c=0.5, Ls=ls, boundary_phases=[1.0, 1.0, 1.0, -1.0])
+    s_np = rng.cnormal([ls] + dims, (4, 3))
+    t0 = time.time()
+    ref, hist = qcd.solve_eo2_ne(qcd.mobius(U, **params), s_np, eps, 1000)
+    t_cpu = time.time() - t0
+    grid = g.grid(dims, g.double)
+    op = g.qcd.fermion.mobius(g.qcd.gauge.from_numpy(grid, [u.reshape(-1, 3, 3) for u in U]), dict(params))
+    src = g.vspincolor(op.F_grid)
+    src[:] = s_np.reshape(-1, 4, 3)
+    inv = g.algorithms.inverter
+    cg = inv.cg(eps=eps, maxiter=1000)
+    slv = inv.preconditioned(g.qcd.fermion.preconditioner.eo2_ne(), cg)(op)
+    g.cgpt.accelerator_barrier()
+    t0 = time.time()
+    dst = g(slv * src)
+    g.cgpt.accelerator_barrier()
+    t_gpu = time.time() - t0
+    r = g(op * dst - src)
+    x = dst[:].reshape(ref.shape)
+    return {"lattice": dims + [ls], "eps": eps, "gpu_seconds": t_gpu, "gpu_iterations": len(cg.history),
+            "gpu_true_residual": float((g.norm2(r) / g.norm2(src)) ** 0.5),
+            "cpu_seconds": t_cpu, "cpu_iterations": len(hist), "cpu_kind": "numpy oracle (oracle/qcd.py), 1 process",
+            "solution_rel_diff": float(np.linalg.norm(x - ref) / np.linalg.norm(ref))}
+
+
 def cpu_baseline(sample_dims, seconds, steps=None, warmup=1):
-    """C/OpenMP restatement of Dhop (oracle/dslash_ref.c) on the host cores, bounded sample of the workload"""
+    """C/OpenMP restatement of Dhop (oracle/dslash_ref.c) on ALL host cores (torchrun exports OMP_NUM_THREADS=1, so the
+    thread count is set explicitly), a bounded number of applications on the bench lattice"""
     from oracle import cref
 
+    cref.set_num_threads(cref.host_cores())
     rs = np.random.default_rng(7)
     v4 = int(np.prod(sample_dims))
-    # cheap unitary links: first-order exp is enough for a throughput sample; normalisation does not matter
+    # cheap unitary links: second-order exp is enough for a throughput sample; normalisation does not matter
     T = gell_mann_half()
     V = np.empty((4, v4, 3, 3), dtype=np.complex64)
     for mu in range(4):
         u = (rs.random((v4, 8), dtype=np.float32) - 0.5) * 0.5
         A = np.einsum("na,aij->nij", u.astype(np.complex64), T)
         V[mu] = np.eye(3, dtype=np.complex64) + 1j * A - 0.5 * (A @ A)
-    psi = (rs.standard_normal((v4 * LS, 4, 3), dtype=np.float32) + 1j * rs.standard_normal((v4 * LS, 4, 3), dtype=np.float32)).astype(np.complex64)
+    psi = rs.standard_normal((v4 * LS, 4, 3, 2), dtype=np.float32).view(np.complex64).reshape(v4 * LS, 4, 3)
     for _ in range(warmup):
         cref.dhop(sample_dims, LS, V, psi)
     t0 = time.time()
@@ -314,24 +547,24 @@ def cpu_baseline(sample_dims, seconds, steps=None, warmup=1):
     except Exception:
         pass
     return {"value": gf, "unit": "GFlop/s", "cores": cref.num_threads(), "kind": "port",
-            "sample": f"{n} applications of Dhop on {sample_dims} Ls={LS} single (oracle/dslash_ref.c, OpenMP; Grid unavailable)",
+            "sample": f"{n} applications of Dhop on {list(sample_dims)} Ls={LS} single (oracle/dslash_ref.c, OpenMP; Grid unavailable)",
             "ms_per_step": dt * 1e3, "cpu": cpu_model, "nproc": os.cpu_count()}
 
 
 def run_reference(args):
-    """reference arm: the CPU restatement of the reference's Dhop on the host cores (Grid cannot be built here)"""
+    """reference arm: the CPU restatement of the reference's Dhop on all host cores (Grid cannot be built here), on the
+    same lattice as the native arm; under torchrun rank 0 alone runs it"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    dims = [16, 16, 16, 32]
-    c = cpu_baseline(dims, seconds=None, steps=args.steps, warmup=max(args.warmup, 1))
+    c = cpu_baseline(DIMS, seconds=None, steps=args.steps, warmup=max(min(args.warmup, 2), 1))
     out = {
         "impl": "reference", "metric": "mobius_dwf_dslash_gflops", "value": c["value"], "unit": "GFlop/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": c["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "Mobius DWF Dhop 32^3x64 Ls=12 single per GPU (BASELINE.json configs[2]); each step is a bounded "
-                               f"sample: one Dhop on {dims} Ls={LS}", "Ls": LS},
-        "cpu_baseline": {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "config": {"workload": WORKLOAD, "local_dims": DIMS, "Ls": LS,
+                   "note": "each step = one Dhop on the full 32^3x64 Ls=12 lattice on the host cores (one lattice, whatever --gpus says)"},
+        "cpu_baseline": {k: c[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu", "nproc")},
         "e2e": {"value": c["value"], "unit": "GFlop/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out))
@@ -340,13 +573,21 @@ def run_reference(args):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--preheat", type=float, default=2.0, help="seconds the loop runs untimed before the K timed steps")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-cg", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-kernels", action="store_true")
+    ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--cg-iterations", type=int, default=50)
+    ap.add_argument("--solve-eps", type=float, default=1e-8)
+    ap.add_argument("--solve-eps-single", type=float, default=1e-6)
+    ap.add_argument("--solve-maxiter", type=int, default=1500)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

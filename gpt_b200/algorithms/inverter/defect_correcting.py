@@ -1,4 +1,14 @@
-"""inv.defect_correcting (lib/gpt/algorithms/inverter/defect_correcting.py:73-139)"""
+"""
+inv.defect_correcting(inner_inverter, eps, maxiter): iterative refinement.
+
+    x_{i+1} = x_i + inner(b - A x_i)
+
+with `inner` an approximate inverse of A -- in practice inv.mixed_precision(...) of an even-odd CG, so that the defect is
+formed in double precision while the iterations run in single (the stack of /root/reference/tests/manual/mpi.py:104-110).
+Observable behaviour follows lib/gpt/algorithms/inverter/defect_correcting.py:73-139: history[i] = |b - A x_i| / |b| measured
+BEFORE the i-th correction, convergence when that drops below eps, the defect handed to the inner solver normalised by |b|
+(single precision would underflow on small defects otherwise), and |A x_0| (or 1) standing in for |b| when b = 0.
+"""
 import gpt_b200 as g
 from gpt_b200.algorithms.base import base_iterative
 
@@ -7,34 +17,33 @@ class defect_correcting(base_iterative):
     @g.params_convention(eps=1e-15, maxiter=1000000)
     def __init__(self, inner_inverter, params):
         super().__init__()
-        self.params = params
-        self.eps = params["eps"]
-        self.maxiter = params["maxiter"]
-        self.inner_inverter = inner_inverter
+        self.params, self.inner_inverter = params, inner_inverter
+        self.eps, self.maxiter = params["eps"], params["maxiter"]
+
+    @staticmethod
+    def _scale_of(src, outer_mat, psi):
+        for candidate in (lambda: g.norm2(src), lambda: g.norm2(g(outer_mat * psi))):
+            n2 = candidate()
+            if n2 != 0.0:
+                return n2**0.5
+        return 1.0
 
     def __call__(self, outer_mat):
-        inner_inv_mat = self.inner_inverter(outer_mat)
+        approximate_inverse = self.inner_inverter(outer_mat)
 
         @self.timed_function
-        def inv(psi, src, t):
-            _s = g.lattice(src)
-            norm2_of_source = g.norm2(src)
-            if norm2_of_source == 0.0:
-                norm2_of_source = g.norm2(g(outer_mat * psi))
-                if norm2_of_source == 0.0:
-                    norm2_of_source = 1.0
+        def solve(psi, src, t):
+            scale = self._scale_of(src, outer_mat, psi)
+            defect = g.lattice(src)
             for i in range(self.maxiter):
-                _s @= src - outer_mat * psi  # remaining src
-                norm2_of_defect = g.norm2(_s)
-                eps = (norm2_of_defect / norm2_of_source) ** 0.5
-                self.log_convergence(i, eps, self.eps)
-                if eps < self.eps:
+                defect @= src - outer_mat * psi
+                relative = g.norm2(defect) ** 0.5 / scale
+                self.log_convergence(i, relative, self.eps)
+                if relative < self.eps:
                     self.log(f"converged after {i} iterations")
-                    break
-                # normalize _s to avoid floating-point underflow in inner_inv_mat
-                _s /= norm2_of_source**0.5
-                _d = inner_inv_mat(_s)
-                psi += _d * norm2_of_source**0.5
+                    return
+                defect /= scale
+                psi += approximate_inverse(defect) * scale
 
         vector_space = outer_mat.vector_space if isinstance(outer_mat, g.matrix_operator) else None
-        return g.matrix_operator(mat=inv, inv_mat=outer_mat, vector_space=vector_space, accept_guess=(True, False))
+        return g.matrix_operator(mat=solve, inv_mat=outer_mat, vector_space=vector_space, accept_guess=(True, False))

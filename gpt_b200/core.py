@@ -74,7 +74,7 @@ class redblack:
 class grid:
     """g.grid(fdimensions, precision, cb=full): 4d [x,y,z,t] or 5d [s,x,y,z,t] (s never checkerboarded)."""
 
-    _serial = 0
+    _tags = {}
 
     def __init__(self, fdimensions, precision, cb=None, parent=None, mpi=None):
         self.fdimensions = [int(x) for x in fdimensions]
@@ -96,9 +96,11 @@ class grid:
         self.ldimensions = self.fdimensions[:-4] + parallel.local_dims(self.fdimensions[-4:], mpi4)
         self.gsites = int(np.prod(self.fdimensions))
         self.obj = self  # cgpt grid handles are not needed: a lattice carries its geometry
-        # every grid OBJECT owns its set of parallel generators inside a g.random (engine.h:82-99)
-        grid._serial += 1
-        self.serial = grid._serial
+        # a g.random keeps one set of parallel generators per GridBase* and cgpt interns grids by their tag
+        # (fdimensions, simd layout = precision, cb mask, mpi: lib/cgpt/lib/grid.h:33-48, random/engine.h:82-99), so grids
+        # that compare equal share a stream: a second g.grid(...) of the same shape continues it
+        tag = (tuple(self.fdimensions), precision.__name__, self.cb.n, tuple(self.mpi))
+        self.serial = grid._tags.setdefault(tag, len(grid._tags) + 1)
 
     @property
     def dims4(self):
@@ -148,6 +150,20 @@ class grid:
     @property
     def lsites(self):
         return int(np.prod(self.ldimensions))
+
+
+def _local_site(gr, pos):
+    """global coordinates -> lexicographic index (dimension 0 fastest) into this rank's block, or None if another rank owns the site"""
+    from gpt_b200 import parallel
+
+    coor = ([0] if gr.nd == 5 else []) + list(parallel.processor_coor(parallel.rank, parallel.mpi))
+    idx = 0
+    for d in reversed(range(gr.nd)):
+        x = int(pos[d]) % gr.fdimensions[d] - coor[d] * gr.ldimensions[d]
+        if x < 0 or x >= gr.ldimensions[d]:
+            return None
+        idx = idx * gr.ldimensions[d] + x
+    return idx
 
 
 # ---- object types ----------------------------------------------------------------------------------------------
@@ -223,10 +239,9 @@ class lattice:
             return a
         if isinstance(key, tuple) and len(key) == self.grid.nd and all(isinstance(k, (int, np.integer)) for k in key):
             assert self.grid.cb.n == 1
-            idx = 0
-            for d in reversed(range(self.grid.nd)):
-                idx = idx * self.grid.fdimensions[d] + int(key[d])
-            return a[idx]
+            idx = _local_site(self.grid, key)
+            v = a[idx].astype(np.complex128) if idx is not None else np.zeros(a.shape[1:], np.complex128)
+            return np.asarray(self.grid.globalsum(v)).astype(a.dtype).reshape(a.shape[1:])
         raise NotImplementedError("lattice[...] supports [:] and full-lattice point access")
 
     def __setitem__(self, key, value):
@@ -240,12 +255,11 @@ class lattice:
             cgpt.lattice_import(self.obj, np.ascontiguousarray(a, dtype=self.grid.precision.complex_dtype))
             return
         if isinstance(key, tuple) and len(key) == self.grid.nd:
-            a = self[:]
-            idx = 0
-            for d in reversed(range(self.grid.nd)):
-                idx = idx * self.grid.fdimensions[d] + int(key[d])
-            a[idx] = np.asarray(value, dtype=a.dtype).reshape(a[idx].shape)
-            cgpt.lattice_import(self.obj, a)
+            idx = _local_site(self.grid, key)
+            if idx is not None:  # the rank that owns the site
+                a = self[:]
+                a[idx] = np.asarray(value, dtype=a.dtype).reshape(a[idx].shape)
+                cgpt.lattice_import(self.obj, a)
             return
         raise NotImplementedError("lattice[...] = supports [:] and full-lattice point access")
 
@@ -716,10 +730,15 @@ def trace(x):
 def slice(x, dim):  # noqa: A001  (GPT's name)
     """g.slice(g.trace(a * g.adj(b)), 3) -> list of complex per time slice (lib/gpt/core/transform.py:170-171)"""
     if isinstance(x, _trace_ab_dagger) and dim == 3:
-        nt = x.a.grid.fdimensions[-1]
+        from gpt_b200 import parallel
+
+        gr = x.a.grid
+        nt, lt = gr.fdimensions[-1], gr.ldimensions[-1]
+        t0 = parallel.processor_coor(parallel.rank, parallel.mpi)[3] * lt  # first global time slice of this rank's block
         acc = np.zeros(nt, dtype=np.complex128)
         for ca, cb_ in zip(x.a.columns, x.b.columns):
-            acc += cgpt.lattice_slice_inner_product(cb_.obj, ca.obj, nt)
+            acc[t0:t0 + lt] += cgpt.lattice_slice_inner_product(cb_.obj, ca.obj, lt)
+        acc = np.asarray(gr.globalsum(acc))  # ranks split in y / z hold partial sums of the same slices
         return [builtins.complex(v) for v in acc]
     raise NotImplementedError("g.slice is implemented for g.trace(a * g.adj(b)) along time")
 
@@ -730,12 +749,11 @@ class _create:
         """g.create.point(src, pos): unit spin-colour matrix at `pos`, zero elsewhere (lib/gpt/create/point.py)"""
         assert isinstance(src, mspincolor)
         gr = src.grid
-        idx = 0
-        for d in reversed(range(gr.nd)):
-            idx = idx * gr.fdimensions[d] + int(pos[d])
+        idx = _local_site(gr, pos)  # None on the ranks that do not own the site
         for j, col in enumerate(src.columns):
             a = np.zeros((gr.lsites, 4, 3), dtype=gr.precision.complex_dtype)
-            a.reshape(gr.lsites, 12)[idx, j] = 1.0
+            if idx is not None:
+                a.reshape(gr.lsites, 12)[idx, j] = 1.0
             col[:] = a
         return src
 

@@ -70,8 +70,10 @@ __device__ __forceinline__ void acc_dot(double& re, double& im, double2 a, doubl
 
 // r = a x + y, optionally |r|^2
 template <typename T, bool NORM>
-__global__ void __launch_bounds__(BT) k_axpy(size_t nvec, T ar, T ai, const typename V<T>::vec* __restrict__ x,
-                                             const typename V<T>::vec* __restrict__ y, typename V<T>::vec* __restrict__ r,
+// r may alias x and / or y (cg.py: axpy(r, -a, mmp, r), axpy(p, b, p, r)): element-wise, so that is well defined as long as
+// no pointer carries __restrict__ (the loads must not be moved to the read-only path)
+__global__ void __launch_bounds__(BT) k_axpy(size_t nvec, T ar, T ai, const typename V<T>::vec* x,
+                                             const typename V<T>::vec* y, typename V<T>::vec* r,
                                              double* __restrict__ partial) {
   typedef typename V<T>::vec vec;
   double s = 0.0;
@@ -159,8 +161,9 @@ struct LcArgs {
   int n;
 };
 
+// dst may be one of the inputs (psi += a p; lattice *= a): no __restrict__
 template <typename T, bool ACC>
-__global__ void __launch_bounds__(BT) k_lc(size_t nvec, LcArgs<T> args, typename V<T>::vec* __restrict__ dst) {
+__global__ void __launch_bounds__(BT) k_lc(size_t nvec, LcArgs<T> args, typename V<T>::vec* dst) {
   typedef typename V<T>::vec vec;
   size_t stride = (size_t)gridDim.x * BT;
   for (size_t i = (size_t)blockIdx.x * BT + threadIdx.x; i < nvec; i += stride) {
@@ -286,11 +289,19 @@ static void lc_t(cgptb_lattice* dst, int accumulate, int n, const double* coef, 
     blas_zero(dst);
     return;
   }
+  // more than MAXT terms go in chunks that accumulate into dst: a term beyond the first chunk that IS dst must see the
+  // value dst had on entry, so it is read from a copy
+  void* snapshot = 0;
+  for (int t = MAXT; t < n && !snapshot; t++)
+    if (a[t]->data == dst->data) {
+      CUDA_CHECK(cudaMallocAsync(&snapshot, dst->bytes(), g_stream));
+      CUDA_CHECK(cudaMemcpyAsync(snapshot, dst->data, dst->bytes(), cudaMemcpyDeviceToDevice, g_stream));
+    }
   while (done < n) {
     LcArgs<T> args;
     args.n = (n - done) < MAXT ? (n - done) : MAXT;
     for (int t = 0; t < args.n; t++) {
-      args.a[t] = (const vec*)a[done + t]->data;
+      args.a[t] = (const vec*)((snapshot && done > 0 && a[done + t]->data == dst->data) ? snapshot : a[done + t]->data);
       args.cr[t] = (T)coef[2 * (done + t)];
       args.ci[t] = (T)coef[2 * (done + t) + 1];
     }
@@ -302,6 +313,7 @@ static void lc_t(cgptb_lattice* dst, int accumulate, int n, const double* coef, 
     done += args.n;
     acc = true;
   }
+  if (snapshot) CUDA_CHECK(cudaFreeAsync(snapshot, g_stream));
 }
 
 void blas_lc(cgptb_lattice* dst, int accumulate, int n, const double* coef, const cgptb_lattice* const* a) {

@@ -87,6 +87,9 @@ static cgptb_lattice* pipe_field(cgptb_lattice*& slot, const cgptb_fermion_opera
 static bool pipeline_usable(const cgptb_fermion_operator* op, int opcode, int nslab) {
   if (getenv("CGPTB_NO_HOSTPIPE")) return false;
   if (opcode != 3001 && opcode != 4001) return false;  // Dhop, DhopDag (register.h:13-14)
+  // open boundary conditions in time: op_dhop clears the two boundary slices after the stencil (P D P); the slab pipeline
+  // exports slabs as they finish, so these operators take the import -> op_apply -> export path
+  if (op->open_bc) return false;
   // a lattice split in t only keeps every hop of the interior slabs on this rank; the first and the last slab go through
   // the regular halo exchange at the end
   if (!dhop_tma_usable(op) || (op->g.comm_mask & ~8)) return false;

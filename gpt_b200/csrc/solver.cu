@@ -155,7 +155,9 @@ int cgptb_cg_eo2_ne(cgptb_fermion_operator* op, cgptb_lattice* psi, const cgptb_
   if (cgptb_lattice_norm2(src, &n2)) CGPTB_ERR("%s", cgptb_last_error());
   double ssq = n2;
   if (ssq == 0.0) {
+    // cg.py:67-69: a zero source gives psi = 0 and returns silently -- not a convergence failure
     blas_zero(psi);
+    *converged = 1;
     return 0;
   }
   double rsq = eps * eps * ssq;

@@ -104,6 +104,46 @@ static const int RP[4][2] = {{1, 1}, {2, 0}, {1, 3}, {2, 2}};
 DEFINE_DHOP(oracle_dhop_f, float)
 DEFINE_DHOP(oracle_dhop_d, double)
 
+/* The same hopping term on a LIST of 4d sites only (all s): out[(i*ls + s)*24 ...] for sites[i].  bench.py uses it to
+   check the GPU result on >= 1e5 sampled sites of the full-size lattice (and of every rank's block of a split
+   lattice, padded with the neighbours' boundary slices) without paying for a full CPU application.             */
+#define DEFINE_DHOP_SITES(NAME, HOP, REAL)                                                                        \
+  void NAME(const int* dims, int Ls, const REAL* V, const double* coef, const REAL* in, long n, const long* sites, \
+            REAL* out, int dag) {                                                                                 \
+    const long Lx = dims[0], Ly = dims[1], Lz = dims[2], Lt = dims[3];                                            \
+    const long V4 = Lx * Ly * Lz * Lt;                                                                            \
+    const long ls = Ls > 0 ? Ls : 1;                                                                              \
+    _Pragma("omp parallel for schedule(static)") for (long i = 0; i < n; i++) {                                   \
+      const long x4 = sites[i];                                                                                   \
+      long c[4] = {x4 % Lx, (x4 / Lx) % Ly, (x4 / (Lx * Ly)) % Lz, x4 / (Lx * Ly * Lz)};                          \
+      const long L[4] = {Lx, Ly, Lz, Lt};                                                                         \
+      const long stride[4] = {1, Lx, Lx * Ly, Lx * Ly * Lz};                                                      \
+      for (long s = 0; s < ls; s++) {                                                                             \
+        REAL acc[24];                                                                                             \
+        memset(acc, 0, sizeof(acc));                                                                              \
+        for (int mu = 0; mu < 4; mu++) {                                                                          \
+          long xp = x4 + (c[mu] + 1 == L[mu] ? -(L[mu] - 1) : 1) * stride[mu];                                    \
+          long xm = x4 + (c[mu] == 0 ? (L[mu] - 1) : -1) * stride[mu];                                            \
+          REAL w = (REAL)(-0.5 * coef[mu]);                                                                       \
+          HOP(acc, in + (xp * ls + s) * 24, V + ((size_t)mu * V4 + x4) * 18, 0, mu, dag ? +1 : -1, w);            \
+          HOP(acc, in + (xm * ls + s) * 24, V + ((size_t)mu * V4 + xm) * 18, 1, mu, dag ? -1 : +1, w);            \
+        }                                                                                                         \
+        memcpy(out + (i * ls + s) * 24, acc, sizeof(acc));                                                        \
+      }                                                                                                           \
+    }                                                                                                             \
+  }
+
+DEFINE_DHOP_SITES(oracle_dhop_sites_f, oracle_dhop_f_hop, float)
+DEFINE_DHOP_SITES(oracle_dhop_sites_d, oracle_dhop_d_hop, double)
+
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

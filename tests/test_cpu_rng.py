@@ -73,8 +73,20 @@ def test_product_rng_grid_objects_and_errors():
     g1, g2 = g.grid([4, 4, 4, 4], g.double), g.grid([4, 4, 4, 4], g.single)
     a = rng.host_array(g1, 1, NORMAL)
     b = rng.host_array(g2, 1, NORMAL)
-    assert np.array_equal(a, b)  # every grid object starts from the seed (engine.h:82-99; simple.py:19-20)
-    assert not np.array_equal(a, rng.host_array(g1, 1, NORMAL))
+    assert np.array_equal(a, b)  # a grid of another precision is another GridBase*: it starts from the seed (engine.h:82-99; simple.py:19-20)
+    a2 = rng.host_array(g1, 1, NORMAL)
+    assert not np.array_equal(a, a2)
+    # cgpt interns grids by (fdimensions, simd, cb, mpi) (lib/cgpt/lib/grid.h:33-82): a second grid OBJECT of the same shape is the
+    # same GridBase* and continues the stream instead of repeating it
+    g3 = g.grid([4, 4, 4, 4], g.double)
+    assert g3 == g1 and g3 is not g1
+    a3 = rng.host_array(g3, 1, NORMAL)
+    assert not np.array_equal(a3, a) and not np.array_equal(a3, a2)
+    orng = oracle_random("abc")
+    ref = [orng.normal([4, 4, 4, 4]).reshape(-1, 1) for _ in range(3)]
+    for got, want in zip([a, a2, a3], ref):
+        assert np.max(np.abs(got - want)) < 1e-14
+    assert g1.converted(g.single).serial == g2.serial and g1.checkerboarded(g.redblack).serial != g1.serial
     with pytest.raises(RuntimeError):
         g.random("abc", "no such engine")
     with pytest.raises(ValueError):
