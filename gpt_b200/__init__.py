@@ -12,6 +12,8 @@ from gpt_b200 import algorithms, qcd
 from gpt_b200.random import random  # noqa: F401
 from gpt_b200.gamma import gamma  # noqa: F401
 from gpt_b200.io import load, save, format  # noqa: F401,A004
+from gpt_b200 import default  # noqa: F401
+from gpt_b200.timer import timer  # noqa: F401
 import sys as _sys
 
 

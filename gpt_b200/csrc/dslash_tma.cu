@@ -26,6 +26,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <map>
+#include <utility>
+#include <vector>
 #include "dslash.cuh"
 #include "operator.cuh"
 #include "packed.cuh"
@@ -57,11 +60,20 @@ constexpr int STAGE_B = SLOT_B + 2 * LINK_HALF_B;  // 100352
 constexpr int BAR_FC = 0, BAR_FA = 1, BAR_FB = 2, BAR_EA = 3, BAR_EB = 4, NBAR = 5;
 constexpr int SMEM_B = NSLOT * STAGE_B + NSLOT * NBAR * 8 + 1024;  // + alignment slack
 
+// One unit of work: a tile x a chunk of the fifth dimension x a range of time slices.  The host lays the items out so that
+// item i runs on CTA i % gridDim.x ("rounds" of gridDim.x concurrent items that walk t in lock-step, see build_schedule).
+struct __align__(16) ItemDesc {
+  int c, xh0, y0, z0;   // chunk index, tile origin
+  int t0, trl;          // first output time slice, number of output time slices
+  int flags;            // L2 hints for the tile's z sides (KEEP_* / LAST_*), see build_schedule
+  int pad;
+};
+enum { KEEP_TOP = 1, KEEP_BOTTOM = 2, LAST_TOP = 4, LAST_BOTTOM = 8 };
+
 struct Geo {
   int hx, Ly, Lz, T;
   int nbx, nby, nbz, nchunk;
-  int trl, ntr, nitems;
-  int t_begin;  // first time slice of this launch (a launch may cover a slab of the lattice only: hostpipe.cu)
+  int nitems;
   int tp;  // component-plane stride of the input field in units of time slices
   int p_out;
   int ls;
@@ -198,22 +210,6 @@ __device__ __forceinline__ void hop_smem(c32 (&acc)[12], uint32_t spinor_addr, u
   hop_math<MU, FWD, DAG>(acc, psi, wr, wi);
 }
 
-struct Item {
-  int c, xh0, y0, z0, t0;
-};
-__device__ __forceinline__ Item decode_item(const Geo& G, int item) {
-  Item it;
-  it.c = item % G.nchunk;
-  int r = item / G.nchunk;
-  it.xh0 = (r % G.nbx) * TX;
-  r /= G.nbx;
-  it.y0 = (r % G.nby) * TY;
-  r /= G.nby;
-  it.z0 = (r % G.nbz) * TZ;
-  it.t0 = G.t_begin + (r / G.nbz) * G.trl;
-  return it;
-}
-
 // ABL (ablation, CGPTB_ABLATE): 0 production; 1 compute only (no TMA loads, the ring is signalled empty-handed);
 // 2 memory only (all loads and stores, no hop arithmetic)
 // COMM: the lattice is split across GPUs in z and/or t (Geo::comm_mask); off-rank hops are skipped here and added by
@@ -222,7 +218,8 @@ template <bool DAG, int ABL, bool COMM>
 __global__ void __launch_bounds__(NTHREADS, 1)
     k_dhop_f32_tma(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                    const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmM,
-                   const __grid_constant__ CUtensorMap tmL, const Geo G, float* __restrict__ out, size_t out_stride) {
+                   const __grid_constant__ CUtensorMap tmL, const Geo G, const ItemDesc* __restrict__ items,
+                   float* __restrict__ out, size_t out_stride) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t s_bar = sbase + NSLOT * STAGE_B;
@@ -252,20 +249,43 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     // optional L2 eviction priorities (CGPTB_TMA_HINT): the z faces of a tile are the z-boundary layers of the tiles above and
     // below, which are swept one "round" of CTAs earlier or later.  Measured on B200: evict_last on these lines does not
     // change the DRAM traffic (2.47 vs 2.50 GB read per launch) and evict_first on the rest hurts (2.95 GB): default off.
-    const uint64_t pol_keep = G.hint ? L2_EVICT_LAST : L2_EVICT_NORMAL;
-    const uint64_t pol_rest = G.hint == 2 ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
+    //
+    // CGPTB_TMA_HINT >= 3, per item (ItemDesc::flags): only the z sides of a tile that face a tile of the NEXT round keep
+    // their lines (the top layer of the centre box, mode 4; and the z face beyond it, which is the next round's bottom layer,
+    // mode 3), and the round that consumes them reads them with evict_first, so at most two (x,y) planes x T stay resident.
     uint32_t g = 0;
     for (int item = blockIdx.x; item < G.nitems; item += gridDim.x) {
-      const Item it = decode_item(G, item);
+      const ItemDesc it = items[item];
       const int s0f = it.c * SC * 8;
+      uint64_t pol_rest = G.hint == 2 ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
+      uint64_t pol_ctop = (G.hint == 1 || G.hint == 2) ? L2_EVICT_LAST : L2_EVICT_NORMAL, pol_cbot = pol_ctop, pol_zp = pol_ctop,
+               pol_zm = pol_ctop;
+      if (G.hint >= 3) {
+        if (it.flags & KEEP_TOP) {
+          pol_ctop = L2_EVICT_LAST;
+          if (G.hint == 3) pol_zp = L2_EVICT_LAST;
+        }
+        if (it.flags & KEEP_BOTTOM) {
+          pol_cbot = L2_EVICT_LAST;
+          if (G.hint == 3) pol_zm = L2_EVICT_LAST;
+        }
+        if (it.flags & LAST_BOTTOM) {
+          pol_zm = L2_EVICT_FIRST;
+          if (G.hint == 3) pol_cbot = L2_EVICT_FIRST;
+        }
+        if (it.flags & LAST_TOP) {
+          pol_zp = L2_EVICT_FIRST;
+          if (G.hint == 3) pol_ctop = L2_EVICT_FIRST;
+        }
+      }
       const int xm = (it.xh0 == 0 ? G.hx : it.xh0) - 1, xp = it.xh0 + TX == G.hx ? 0 : it.xh0 + TX;
       const int ym = (it.y0 == 0 ? G.Ly : it.y0) - 1, yp = it.y0 + TY == G.Ly ? 0 : it.y0 + TY;
       const int zm = (it.z0 == 0 ? G.Lz : it.z0) - 1, zp = it.z0 + TZ == G.Lz ? 0 : it.z0 + TZ;
-      for (int st = 0; st <= G.trl + 1; st++, g++) {
+      for (int st = 0; st <= it.trl + 1; st++, g++) {
         int tau = it.t0 - 1 + st;
         if (tau < 0) tau += G.T;
         if (tau >= G.T) tau -= G.T;
-        const bool full_step = st >= 1 && st <= G.trl;
+        const bool full_step = st >= 1 && st <= it.trl;
         const uint32_t slot = g & 1u, ph = (g >> 1) & 1u;
         const uint32_t bar = s_bar + 8 * NBAR * slot;
         const uint32_t dst = sbase + slot * STAGE_B;
@@ -303,9 +323,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             // centre box as bottom layer, two middle layers, top layer (rows [z][y][x]: 16 rows per layer)
             const uint32_t d = dst + k * PLANE_B + OFF_C;
             const int tq = k * G.tp + tau;
-            tma_load_5d_hint(d, &tmZ, bar + 8 * BAR_FC, s0f, it.xh0, it.y0, it.z0, tq, pol_keep);
+            tma_load_5d_hint(d, &tmZ, bar + 8 * BAR_FC, s0f, it.xh0, it.y0, it.z0, tq, pol_cbot);
             tma_load_5d_hint(d + 16 * ROW_B, &tmM, bar + 8 * BAR_FC, s0f, it.xh0, it.y0, it.z0 + 1, tq, pol_rest);
-            tma_load_5d_hint(d + 48 * ROW_B, &tmZ, bar + 8 * BAR_FC, s0f, it.xh0, it.y0, it.z0 + 3, tq, pol_keep);
+            tma_load_5d_hint(d + 48 * ROW_B, &tmZ, bar + 8 * BAR_FC, s0f, it.xh0, it.y0, it.z0 + 3, tq, pol_ctop);
           }
           if (full_step && bytesB != 0) {
             mbar_expect_tx(bar + 8 * BAR_FB, bytesB);
@@ -317,8 +337,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
               const uint32_t d = dst + k * PLANE_B;
               if (!(G.skip & 2)) tma_load_5d_hint(d + OFF_YM, &tmY, bar + 8 * BAR_FB, s0f, it.xh0, ym, it.z0, tq, pol_rest);
               if (!(G.skip & 4)) {
-                tma_load_5d_hint(d + OFF_ZP, &tmZ, bar + 8 * BAR_FB, s0f, it.xh0, it.y0, zp, tq, pol_keep);
-                tma_load_5d_hint(d + OFF_ZM, &tmZ, bar + 8 * BAR_FB, s0f, it.xh0, it.y0, zm, tq, pol_keep);
+                tma_load_5d_hint(d + OFF_ZP, &tmZ, bar + 8 * BAR_FB, s0f, it.xh0, it.y0, zp, tq, pol_zp);
+                tma_load_5d_hint(d + OFF_ZM, &tmZ, bar + 8 * BAR_FB, s0f, it.xh0, it.y0, zm, tq, pol_zm);
               }
             }
           } else {
@@ -353,15 +373,15 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 
   uint32_t g = 0;
   for (int item = blockIdx.x; item < G.nitems; item += gridDim.x) {
-    const Item it = decode_item(G, item);
+    const ItemDesc it = items[item];
     const int site0 = (it.xh0 + lx) + G.hx * ((it.y0 + ly) + G.Ly * (it.z0 + lz));
     const int s = it.c * SC + j;
     int tau_prev = 0;
-    for (int st = 0; st <= G.trl + 1; st++, g++) {
+    for (int st = 0; st <= it.trl + 1; st++, g++) {
       int tau = it.t0 - 1 + st;
       if (tau < 0) tau += G.T;
       if (tau >= G.T) tau -= G.T;
-      const bool full_step = st >= 1 && st <= G.trl;
+      const bool full_step = st >= 1 && st <= it.trl;
       const uint32_t slot = g & 1u, ph = (g >> 1) & 1u;
       const uint32_t bar = s_bar + 8 * NBAR * slot;
       const uint32_t sp = sbase + slot * STAGE_B;
@@ -464,6 +484,95 @@ static int env_i(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
+// Work schedule of one launch (item i runs on CTA i % grid; the CTAs of a "round" walk t in lock-step, so the x / y / z
+// neighbours inside a round's set of tiles and the three chunk-CTAs that share a tile's links hit in L2).
+//
+//   sched 1 (default): every (tile, chunk) pair is swept over the WHOLE time range by one CTA -- floor(pairs / grid) full
+//     rounds --, and the pairs that are left share the last round, each split into floor(grid / left) time ranges.  Compared
+//     with fixed ranges of 16 slices (sched 0: 3072 items of 18 steps at 32^3 x 64 x 12) this drops the two extra centre
+//     loads at the ends of a range from 2/16 to ~2/64 of the centre traffic and the number of steps per CTA from 378 to 345.
+//   sched 0: the round-1 schedule, kept for A/B runs (CGPTB_TMA_SCHED=0, range length CGPTB_TMA_TRL).
+//
+// flags (CGPTB_TMA_HINT >= 3): the z sides of a tile whose z neighbour runs one round later (KEEP_*) or ran one round earlier
+// (LAST_*), see the producer.
+static std::vector<ItemDesc> build_schedule(const Geo& G, int grid, int t_begin, int t_count, int sched, int trl_max) {
+  std::vector<ItemDesc> items;
+  const int ntile = G.nbx * G.nby * G.nbz, npairs = ntile * G.nchunk;
+  auto make = [&](int pair, int t0, int trl) {
+    ItemDesc it;
+    it.c = pair % G.nchunk;
+    int r = pair / G.nchunk;
+    it.xh0 = (r % G.nbx) * TX;
+    r /= G.nbx;
+    it.y0 = (r % G.nby) * TY;
+    it.z0 = (r / G.nby) * TZ;
+    it.t0 = t0;
+    it.trl = trl;
+    it.flags = 0;
+    it.pad = 0;
+    return it;
+  };
+  if (sched == 0) {
+    int trl = 1;
+    for (int d = 1; d <= t_count && d <= trl_max; d++)
+      if (t_count % d == 0) trl = d;
+    for (int tr = 0; tr < t_count / trl; tr++)
+      for (int pair = 0; pair < npairs; pair++) items.push_back(make(pair, t_begin + tr * trl, trl));
+    return items;
+  }
+  const int rounds = npairs / grid, left = npairs % grid;
+  auto round_of = [&](int pair) { return pair / grid < rounds ? pair / grid : rounds; };
+  auto with_flags = [&](ItemDesc it, int pair) {
+    if (G.nbz < 2) return it;
+    const int per_z = G.nchunk * G.nbx * G.nby, bz = pair / per_z, rm = round_of(pair);
+    const int up = round_of(pair + ((bz + 1) % G.nbz - bz) * per_z), dn = round_of(pair + ((bz + G.nbz - 1) % G.nbz - bz) * per_z);
+    if (up == rm + 1) it.flags |= KEEP_TOP;
+    if (up == rm - 1) it.flags |= LAST_TOP;
+    if (dn == rm + 1) it.flags |= KEEP_BOTTOM;
+    if (dn == rm - 1) it.flags |= LAST_BOTTOM;
+    return it;
+  };
+  for (int pair = 0; pair < rounds * grid; pair++) items.push_back(with_flags(make(pair, t_begin, t_count), pair));
+  if (left) {
+    int k = grid / left;
+    const int kmax = t_count >= 8 ? t_count / 4 : 1;  // ranges shorter than 4 slices pay too much for their two extra loads
+    if (k > kmax) k = kmax;
+    if (k < 1) k = 1;
+    for (int q = 0; q < left; q++) {
+      const int pair = rounds * grid + q;
+      int t0 = t_begin;
+      for (int j = 0; j < k; j++) {
+        const int trl = t_count / k + (j < t_count % k ? 1 : 0);
+        items.push_back(with_flags(make(pair, t0, trl), pair));
+        t0 += trl;
+      }
+    }
+  }
+  return items;
+}
+
+struct SchedKey {
+  int v[12];
+  bool operator<(const SchedKey& o) const { return memcmp(v, o.v, sizeof(v)) < 0; }
+};
+static std::map<SchedKey, std::pair<ItemDesc*, int>> g_sched;
+
+static const ItemDesc* schedule_on_device(const Geo& G, int grid, int t_begin, int t_count, int sched, int trl_max, int* nitems) {
+  SchedKey key = {{G.hx, G.Ly, G.Lz, G.T, G.nchunk, grid, t_begin, t_count, sched, trl_max, 0, 0}};
+  auto f = g_sched.find(key);
+  if (f == g_sched.end()) {
+    std::vector<ItemDesc> items = build_schedule(G, grid, t_begin, t_count, sched, trl_max);
+    ItemDesc* d = 0;
+    CUDA_CHECK(cudaMalloc(&d, items.size() * sizeof(ItemDesc)));
+    // pageable source: the call returns once the host data has been staged; ordered before the launch on the same stream
+    CUDA_CHECK(cudaMemcpyAsync(d, items.data(), items.size() * sizeof(ItemDesc), cudaMemcpyHostToDevice, g_stream));
+    CUDA_CHECK(cudaStreamSynchronize(g_stream));
+    f = g_sched.emplace(key, std::make_pair(d, (int)items.size())).first;
+  }
+  *nitems = f->second.second;
+  return f->second.first;
+}
+
 }  // namespace tma
 
 // true if the TMA sweep kernel handles this operator / lattice (single GPU, Ls a multiple of 4, extents divisible by
@@ -510,19 +619,11 @@ void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, s
   G.nby = g.L[1] / TY;
   G.nbz = g.L[2] / TZ;
   G.nchunk = ls / SC;
-  const int trl_max = env_i("CGPTB_TMA_TRL", 16);  // time slices per work item: the largest divisor of T below the cap
   if (t_count <= 0) {
     t_begin = 0;
     t_count = G.T;
   }
   CGPTB_ASSERT(t_begin >= 0 && t_begin + t_count <= G.T);
-  int trl = 1;
-  for (int d = 1; d <= t_count && d <= trl_max; d++)
-    if (t_count % d == 0) trl = d;
-  G.trl = trl;
-  G.ntr = t_count / trl;
-  G.t_begin = t_begin;
-  G.nitems = G.nchunk * G.nbx * G.nby * G.nbz * G.ntr;
   const size_t slice_blocks = (size_t)g.hx * g.L[1] * g.L[2] * ls;  // 32-byte blocks per time slice
   CGPTB_ASSERT(in_stride % slice_blocks == 0);
   G.tp = (int)(in_stride / slice_blocks);
@@ -569,10 +670,11 @@ void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, s
   // the stencil is done, so a split lattice leaves a few SMs free for them (CGPTB_TMA_COMM_SMS)
   int grid = grid_env > 0 ? grid_env : sm_count() - (g.comm_mask ? env_i("CGPTB_TMA_COMM_SMS", 8) : 0);
   if (grid < 1) grid = 1;
+  const ItemDesc* items = schedule_on_device(G, grid, t_begin, t_count, env_i("CGPTB_TMA_SCHED", 1), env_i("CGPTB_TMA_TRL", 16), &G.nitems);
   if (grid > G.nitems) grid = G.nitems;
   const int abl = env_i("CGPTB_ABLATE", 0);
 #define TMA_LAUNCH(DAG_, ABL_, COMM_) \
-  k_dhop_f32_tma<DAG_, ABL_, COMM_><<<grid, NTHREADS, SMEM_B, g_stream>>>(tmX, tmY, tmZ, tmM, tmL, G, pout, out_stride)
+  k_dhop_f32_tma<DAG_, ABL_, COMM_><<<grid, NTHREADS, SMEM_B, g_stream>>>(tmX, tmY, tmZ, tmM, tmL, G, items, pout, out_stride)
   if (g.comm_mask) {
     if (dag)
       TMA_LAUNCH(true, 0, true);

@@ -20,9 +20,25 @@ import gpt_b200 as g
 from gpt_b200 import cgpt
 
 
+def synthetic_fields_device(dims, ls, seed):
+    """links = exp(i * 0.5 * sum_a u_a T_a), u_a ~ U[-1/2,1/2); source = N(0,1) + i N(0,1), generated on the device with torch's RNG
+    (quick inputs for A/B runs; bench.py and the tests draw GPT's own RANLUX stream)"""
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(seed)
+    v4 = int(np.prod(dims))
+    T = torch.tensor(bench.gell_mann_half(), dtype=torch.complex64, device="cuda")
+    U = []
+    for mu in range(4):
+        u = torch.rand((v4, 8), generator=gen, device="cuda", dtype=torch.float32) - 0.5
+        A = torch.einsum("na,aij->nij", (0.5 * u).to(torch.complex64), T)
+        U.append(torch.linalg.matrix_exp(1j * A).contiguous())
+    src = torch.randn((v4 * ls, 4, 3, 2), generator=gen, device="cuda", dtype=torch.float32)
+    return U, torch.view_as_complex(src).contiguous()
+
+
 def setup(dims, Ls, seed):
     grid = g.grid(dims, g.single)
-    U_t, src_t = bench.synthetic_fields_device(torch, dims, Ls, seed)
+    U_t, src_t = synthetic_fields_device(dims, Ls, seed)
     U = []
     for mu in range(4):
         u = g.mcolor(grid)
@@ -38,7 +54,7 @@ def setup(dims, Ls, seed):
 
 
 def apply(qm, src, dag, env):
-    for k in ("CGPTB_NO_TMA", "CGPTB_TMA_GRID", "CGPTB_TMA_TRL", "CGPTB_ABLATE"):
+    for k in [k for k in os.environ if k.startswith("CGPTB_")]:
         os.environ.pop(k, None)
     os.environ.update(env)
     dst = g.vspincolor(qm.F_grid)
@@ -58,8 +74,9 @@ def check():
         qm, src = setup(dims, Ls, 11)
         for dag in (False, True):
             ref = apply(qm, src, dag, {"CGPTB_NO_TMA": "1"})
-            for env in ({}, {"CGPTB_TMA_GRID": "1", "CGPTB_TMA_TRL": "2"}, {"CGPTB_TMA_GRID": "5", "CGPTB_TMA_TRL": "4"},
-                        {"CGPTB_TMA_GRID": "3", "CGPTB_TMA_TRL": "1"}, {"CGPTB_TMA_TRL": "64"}):
+            for env in ({}, {"CGPTB_TMA_GRID": "1"}, {"CGPTB_TMA_GRID": "5", "CGPTB_TMA_HINT": "3"}, {"CGPTB_TMA_GRID": "7", "CGPTB_TMA_HINT": "4"},
+                        {"CGPTB_TMA_SCHED": "0", "CGPTB_TMA_GRID": "1", "CGPTB_TMA_TRL": "2"}, {"CGPTB_TMA_SCHED": "0", "CGPTB_TMA_GRID": "5", "CGPTB_TMA_TRL": "4"},
+                        {"CGPTB_TMA_SCHED": "0", "CGPTB_TMA_GRID": "3", "CGPTB_TMA_TRL": "1"}, {"CGPTB_TMA_SCHED": "0", "CGPTB_TMA_TRL": "64"}):
                 got = apply(qm, src, dag, dict(env))
                 err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
                 mx = np.abs(got - ref).max()
@@ -107,9 +124,10 @@ def timing():
     else:
         if os.environ.get("ABLATE"):
             variants += [("tma compute-only", {"CGPTB_ABLATE": "1"}), ("tma memory-only", {"CGPTB_ABLATE": "2"})]
-        for trl in os.environ.get("TRLS", "8,16,32,64").split(","):
-            for grid in os.environ.get("GRIDS", "148").split(","):
-                variants.append((f"tma trl={trl} grid={grid}", {"CGPTB_TMA_TRL": trl, "CGPTB_TMA_GRID": grid}))
+        variants += [("tma sched0 trl16 (round 1)", {"CGPTB_TMA_SCHED": "0"}), ("tma sched1", {}),
+                     ("tma sched1 hint3", {"CGPTB_TMA_HINT": "3"}), ("tma sched1 hint4", {"CGPTB_TMA_HINT": "4"}),
+                     ("tma sched1 grid144", {"CGPTB_TMA_GRID": "144"}), ("tma sched1 grid144 hint3", {"CGPTB_TMA_GRID": "144", "CGPTB_TMA_HINT": "3"}),
+                     ("tma sched1 grid144 hint4", {"CGPTB_TMA_GRID": "144", "CGPTB_TMA_HINT": "4"})]
     steps = int(os.environ.get("STEPS", "200"))
     for rnd in range(int(os.environ.get("ROUNDS", "2"))):
         for name, env in variants:
@@ -126,7 +144,7 @@ def timing():
             ms = cgpt.timer_stop() / steps
             gbs = bytes_per_launch / (ms * 1e-3 / 2) / 1e9
             print(f"TIME {name}: {ms:.4f} ms/step  {gbs:.0f} GB/s  frac {gbs / 6553:.3f}", flush=True)
-    for k in ("CGPTB_NO_TMA", "CGPTB_TMA_GRID", "CGPTB_TMA_TRL", "CGPTB_ABLATE"):
+    for k in [k for k in os.environ if k.startswith("CGPTB_")]:
         os.environ.pop(k, None)
 
 
