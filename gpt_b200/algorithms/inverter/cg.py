@@ -17,7 +17,7 @@ Two execution paths produce that behaviour:
 import os
 
 import gpt_b200 as g
-from gpt_b200 import cgpt
+from gpt_b200 import capi
 from gpt_b200.algorithms.base import base_iterative
 
 
@@ -95,7 +95,7 @@ class cg(base_iterative):
         def solve(psi, src, t):
             assert src != psi
             if device_loop is not None:
-                history, converged = cgpt.cg_eo2_ne(device_loop().interface.obj, psi.obj, src.obj, self.eps, self.maxiter)
+                history, converged = capi.cg_eo2_ne(device_loop().interface.obj, psi.obj, src.obj, self.eps, self.maxiter)
                 self.history.extend(history)
                 if history:  # no iteration at all: zero right-hand side, psi = 0 (silent, like the reference)
                     self._finish(len(history), history[-1], self.eps**2.0 * g.norm2(src) if not converged else 0.0, converged)

@@ -8,7 +8,7 @@ Schur complement two of an even-odd decomposed operator
 import os
 
 import gpt_b200 as g
-from gpt_b200 import cgpt
+from gpt_b200 import capi
 
 
 class schur_complement_two:
@@ -31,7 +31,7 @@ class schur_complement_two:
 
         def _N(o_d, i_d):
             if fused:
-                cgpt.apply_schur_two(op.interface.obj, False, i_d.obj, o_d.obj)
+                capi.apply_schur_two(op.interface.obj, False, i_d.obj, o_d.obj)
                 return
             DD.inv_mat(tmp_d[0], i_d)
             CD.mat(tmp_c[0], tmp_d[0])
@@ -41,7 +41,7 @@ class schur_complement_two:
 
         def _N_dag(o_d, i_d):
             if fused:
-                cgpt.apply_schur_two(op.interface.obj, True, i_d.obj, o_d.obj)
+                capi.apply_schur_two(op.interface.obj, True, i_d.obj, o_d.obj)
                 return
             DC.adj_mat(tmp_c[0], i_d)
             CC.adj_inv_mat(tmp_c[1], tmp_c[0])

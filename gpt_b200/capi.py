@@ -73,6 +73,7 @@ SIGNATURES = {
     "cgptb_lattice_bytes": (c_size_t, [c_void_p]),
     "cgptb_lattice_sites": (c_size_t, [c_void_p]),
     "cgptb_lattice_device_ptr": (c_void_p, [c_void_p]),
+    "cgptb_lattice_info": (c_int, [c_void_p, _pi, _pi, _pi, _pi, _pi]),
     "cgptb_lattice_get_checkerboard": (c_int, [c_void_p]),
     "cgptb_lattice_change_checkerboard": (c_int, [c_void_p, c_int]),
     "cgptb_lattice_set_to_zero": (c_int, [c_void_p]),
@@ -210,6 +211,19 @@ def create_lattice(dims4, Ls, precision, otype, cb, device_ptr=None):
     else:
         _check(_lib_ready().cgptb_create_lattice_view(ctypes.byref(h), d, int(Ls), precision, otype, cb, c_void_p(device_ptr)))
     return h.value
+
+
+def lattice_info(h):
+    d = (c_int * 4)()
+    ls, prec, otype, cb = c_int(), c_int(), c_int(), c_int()
+    _check(_lib_ready().cgptb_lattice_info(c_void_p(h), d, ctypes.byref(ls), ctypes.byref(prec), ctypes.byref(otype), ctypes.byref(cb)))
+    return {"dims4": list(d), "Ls": ls.value, "precision": prec.value, "otype": otype.value, "cb": cb.value}
+
+
+def create_lattice_like(h):
+    """a new lattice of the same grid, precision, object type and checkerboard label"""
+    i = lattice_info(h)
+    return create_lattice(i["dims4"], i["Ls"], i["precision"], i["otype"], i["cb"])
 
 
 def delete_lattice(h):

@@ -10,7 +10,10 @@ and error behaviour follow the reference (file:line relative to /root/reference)
   matrix_operator  lib/gpt/core/operator/matrix_operator.py:35-305
   transforms       lib/gpt/core/transform.py:101-153, core/checkerboard.py:56-81, core/basis.py:66-74
 
-All arithmetic happens in libcgpt_b200.so through gpt_b200.cgpt; this file holds no numerics.
+All arithmetic happens in libcgpt_b200.so.  Calls that exist in the reference's `cgpt` module go through the signature-exact
+stand-in of that module (./cgpt/__init__.py: same names, argument lists and return values, so this file talks to the library
+the way lib/gpt talks to Grid); calls the reference has no counterpart for (host import / export of whole fields, the fused
+kernels) go through `capi`, the ctypes binding of include/cgpt_b200.h.  This file holds no numerics.
 """
 import builtins
 import numbers
@@ -19,7 +22,8 @@ import time as _time
 
 import numpy as np
 
-from gpt_b200 import cgpt
+import cgpt
+from gpt_b200 import capi
 
 
 # ---- precision -----------------------------------------------------------------------------------------
@@ -37,8 +41,8 @@ class _precision:
         return self.__name__
 
 
-single = _precision("single", np.float32, np.complex64, 4, 1e-7, cgpt.SINGLE)
-double = _precision("double", np.float64, np.complex128, 8, 1e-15, cgpt.DOUBLE)
+single = _precision("single", np.float32, np.complex64, 4, 1e-7, capi.SINGLE)
+double = _precision("double", np.float64, np.complex128, 8, 1e-15, capi.DOUBLE)
 
 
 # ---- checkerboards ---------------------------------------------------------------------------------------
@@ -48,16 +52,16 @@ class _cb:
         self.tag = tag
 
     def inv(self):
-        return {cgpt.EVEN: odd, cgpt.ODD: even, cgpt.FULL: none}[self.tag]
+        return {capi.EVEN: odd, capi.ODD: even, capi.FULL: none}[self.tag]
 
     def __repr__(self):
         return self.__name__
 
 
-even = _cb("even", cgpt.EVEN)
-odd = _cb("odd", cgpt.ODD)
-none = _cb("none", cgpt.FULL)
-_cb_of = {cgpt.EVEN: even, cgpt.ODD: odd, cgpt.FULL: none}
+even = _cb("even", capi.EVEN)
+odd = _cb("odd", capi.ODD)
+none = _cb("none", capi.FULL)
+_cb_of = {capi.EVEN: even, capi.ODD: odd, capi.FULL: none}
 
 
 class full:
@@ -74,7 +78,6 @@ class redblack:
 class grid:
     """g.grid(fdimensions, precision, cb=full): 4d [x,y,z,t] or 5d [s,x,y,z,t] (s never checkerboarded)."""
 
-    _tags = {}
 
     def __init__(self, fdimensions, precision, cb=None, parent=None, mpi=None):
         self.fdimensions = [int(x) for x in fdimensions]
@@ -95,12 +98,14 @@ class grid:
         self.Nprocessors = parallel.world
         self.ldimensions = self.fdimensions[:-4] + parallel.local_dims(self.fdimensions[-4:], mpi4)
         self.gsites = int(np.prod(self.fdimensions))
-        self.obj = self  # cgpt grid handles are not needed: a lattice carries its geometry
-        # a g.random keeps one set of parallel generators per GridBase* and cgpt interns grids by their tag
-        # (fdimensions, simd layout = precision, cb mask, mpi: lib/cgpt/lib/grid.h:33-48, random/engine.h:82-99), so grids
-        # that compare equal share a stream: a second g.grid(...) of the same shape continues it
-        tag = (tuple(self.fdimensions), precision.__name__, self.cb.n, tuple(self.mpi))
-        self.serial = grid._tags.setdefault(tag, len(grid._tags) + 1)
+        # cgpt interns grids by (fdimensions, simd layout = precision, cb mask, mpi) (lib/cgpt/lib/grid.h:33-82) and a g.random keeps
+        # one set of parallel generators per grid handle (random/engine.h:82-99): grids that compare equal share a stream, a second
+        # g.grid(...) of the same shape continues it
+        cb_mask = [0] * self.nd
+        if self.cb.n != 1:
+            cb_mask[self.nd - 4] = 1  # red-black grids are checkerboarded along x; the fifth dimension never is (grid.py:31-37)
+        self.obj = cgpt.create_grid(self.fdimensions, precision.cgpt_dtype, cb_mask, [1] * self.nd, self.mpi, 0)
+        self.serial = self.obj
 
     @property
     def dims4(self):
@@ -143,9 +148,10 @@ class grid:
         cgpt.accelerator_barrier()
 
     def globalsum(self, x):
-        from gpt_b200 import parallel
-
-        return parallel.globalsum(x)
+        # lib/gpt/core/global_sum.py:23-31: numbers come back as new values, arrays are summed in place
+        if isinstance(x, (list, tuple)):
+            x = np.array(x)
+        return cgpt.grid_globalsum(self.obj, x)
 
     @property
     def lsites(self):
@@ -173,6 +179,9 @@ class _otype:
         self.shape = shape
         self.nfloats = 2 * int(np.prod(shape)) if shape else 2
         self.code = code
+        # name of the (single) cgpt lattice type that stores this object (lib/gpt/core/object_type: v_otype)
+        self.v_otype = ["ot_matrix_color(3)" if name == "ot_matrix_su_n_fundamental_group(3)" else name]
+        self.v_idx = range(1)
         if name == "ot_matrix_su_n_fundamental_group(3)":
             self.Nc = 3
 
@@ -180,9 +189,9 @@ class _otype:
         return self.__name__
 
 
-ot_singlet = _otype("ot_singlet", (), cgpt.OT_SINGLET)
-ot_matrix_su_n_fundamental_group_3 = _otype("ot_matrix_su_n_fundamental_group(3)", (3, 3), cgpt.OT_MCOLOR)
-ot_vector_spin_color_4_3 = _otype("ot_vector_spin_color(4,3)", (4, 3), cgpt.OT_VSPINCOLOR)
+ot_singlet = _otype("ot_singlet", (), capi.OT_SINGLET)
+ot_matrix_su_n_fundamental_group_3 = _otype("ot_matrix_su_n_fundamental_group(3)", (3, 3), capi.OT_MCOLOR)
+ot_vector_spin_color_4_3 = _otype("ot_vector_spin_color(4,3)", (4, 3), capi.OT_VSPINCOLOR)
 
 
 def ot_vector_spin_color(ns, nc):
@@ -207,9 +216,14 @@ class lattice:
         else:
             self.grid = first
             self.otype = otype
-            cb = cgpt.FULL if first.cb.n == 1 else cgpt.EVEN
+            cb = capi.FULL if first.cb.n == 1 else capi.EVEN
         g = self.grid
-        self.obj = cgpt.create_lattice(g.dims4, g.Ls, g.precision.code, self.otype.code, cb, device_ptr)
+        if device_ptr is None:
+            self.obj = cgpt.create_lattice(g.obj, self.otype.v_otype[0], g.precision.cgpt_dtype)
+            if cb == capi.ODD:
+                cgpt.lattice_change_checkerboard(self.obj, cb)
+        else:  # view of externally owned device memory (library extension)
+            self.obj = capi.create_lattice(g.dims4, g.Ls, g.precision.code, self.otype.code, cb, device_ptr)
         self.v_obj = [self.obj]
 
     def __del__(self):
@@ -220,6 +234,8 @@ class lattice:
     # -- checkerboard label
     def checkerboard(self, val=None):
         if val is None:
+            if self.grid.cb.n == 1:
+                return none
             return _cb_of[cgpt.lattice_get_checkerboard(self.obj)]
         if val is not none:
             assert self.grid.cb.n != 1
@@ -228,13 +244,13 @@ class lattice:
 
     # -- host views in GPT order
     def _host_shape(self):
-        return (int(cgpt.lattice_bytes(self.obj) // (self.otype.nfloats * self.grid.precision.nbytes)),) + tuple(
+        return (int(capi.lattice_bytes(self.obj) // (self.otype.nfloats * self.grid.precision.nbytes)),) + tuple(
             self.otype.shape
         )
 
     def __getitem__(self, key):
         a = np.empty(self._host_shape(), dtype=self.grid.precision.complex_dtype)
-        cgpt.lattice_export(self.obj, a)
+        capi.lattice_export(self.obj, a)
         if isinstance(key, builtins.slice) and key == builtins.slice(None):
             return a
         if isinstance(key, tuple) and len(key) == self.grid.nd and all(isinstance(k, (int, np.integer)) for k in key):
@@ -247,19 +263,19 @@ class lattice:
     def __setitem__(self, key, value):
         if isinstance(key, builtins.slice) and key == builtins.slice(None):
             if isinstance(value, numbers.Number) and value == 0:
-                cgpt.lattice_set_to_zero(self.obj)
+                cgpt.lattice_set_to_number(self.obj, 0.0)
                 return
             a = np.asarray(value)
             if a.shape != self._host_shape() and a.size != int(np.prod(self._host_shape())):
                 raise ValueError(f"shape mismatch: {a.shape} vs {self._host_shape()}")
-            cgpt.lattice_import(self.obj, np.ascontiguousarray(a, dtype=self.grid.precision.complex_dtype))
+            capi.lattice_import(self.obj, np.ascontiguousarray(a, dtype=self.grid.precision.complex_dtype))
             return
         if isinstance(key, tuple) and len(key) == self.grid.nd:
             idx = _local_site(self.grid, key)
             if idx is not None:  # the rank that owns the site
                 a = self[:]
                 a[idx] = np.asarray(value, dtype=a.dtype).reshape(a[idx].shape)
-                cgpt.lattice_import(self.obj, a)
+                capi.lattice_import(self.obj, a)
             return
         raise NotImplementedError("lattice[...] = supports [:] and full-lattice point access")
 
@@ -295,15 +311,15 @@ class lattice:
         return self
 
     def __imul__(self, other):
-        cgpt.lattice_scale(self.obj, other)
+        capi.lattice_scale(self.obj, other)
         return self
 
     def __itruediv__(self, other):
-        cgpt.lattice_scale(self.obj, 1.0 / other)
+        capi.lattice_scale(self.obj, 1.0 / other)
         return self
 
     def global_bytes(self):
-        return int(cgpt.lattice_bytes(self.obj))
+        return int(capi.lattice_bytes(self.obj))
 
 
 def vspincolor(grid_):
@@ -315,6 +331,11 @@ def mcolor(grid_):
 
 
 def complex(grid_):  # noqa: A001  (GPT's name)
+    return lattice(grid_, ot_singlet)
+
+
+def real(grid_):
+    """g.real(grid): GPT stores real fields as complex singlets as well (lib/gpt/core/object_type/__init__.py)"""
     return lattice(grid_, ot_singlet)
 
 
@@ -388,7 +409,9 @@ def eval(first, second=None, ac=False):  # noqa: A001  (GPT's name)
     vals = [(c, _apply_chain(f)) for c, f in e.terms]
     if dst is None:
         dst = lattice(vals[0][1])
-    cgpt.lattice_lc(dst.obj, ac, [c for c, _ in vals], [v.obj for _, v in vals])
+    # the reference's encoding of a linear combination (lib/gpt/core/expr.py:126-143): [(coefficient, [(factor_unary, [lattice])])]
+    terms = [(builtins.complex(c), [(0, [v])]) for c, v in vals]
+    cgpt.eval(dst.v_obj, terms, 0, bool(ac), 0)
     return dst
 
 
@@ -455,9 +478,9 @@ class matrix_operator:
             t_dst = lattice(grid5, dst[0].otype)
             if grid5.cb.n != 1:
                 t_src.checkerboard(src[0].checkerboard())
-            cgpt.lattice_pack_rhs(t_src.obj, [x.obj for x in src])
+            capi.lattice_pack_rhs(t_src.obj, [x.obj for x in src])
             op5(t_dst, t_src)
-            cgpt.lattice_pack_rhs(t_dst.obj, [x.obj for x in dst], unpack=True)
+            capi.lattice_pack_rhs(t_dst.obj, [x.obj for x in dst], unpack=True)
 
         def wrap(get):
             return lambda dst, src: _packed(dst, src, get())
@@ -518,6 +541,11 @@ class matrix_operator:
         return dst
 
 
+class projected_matrix_operator:
+    """lib/gpt/core/operator/projected_matrix_operator.py (gradients projected to the gauge algebra): outside the hot path; the
+    class exists so that `isinstance(x, g.projected_matrix_operator)` in user code is False for every operator of this package"""
+
+
 class matrix_operator_product(matrix_operator):
     def __init__(self, factors):
         self.factors = factors
@@ -572,18 +600,18 @@ def norm2(l):
     if isinstance(l, list):
         return [norm2(x) for x in l]
     l = eval(l)
-    return l.grid.globalsum(cgpt.lattice_norm2(l.obj))
+    return l.grid.globalsum(cgpt.lattice_norm2(l.v_obj[0]))
 
 
 def inner_product(a, b):
     a, b = eval(a), eval(b)
-    return a.grid.globalsum(builtins.complex(cgpt.lattice_rank_inner_product([a.obj], [b.obj])[0, 0]))
+    return a.grid.globalsum(builtins.complex(cgpt.lattice_rank_inner_product([a], [b], 1, 1)[0, 0]))
 
 
-def rank_inner_product(a, b, use_accelerator=True):
-    """rank-local <a,b>; the caller does the global sum (lib/gpt/core/transform.py:101-110)"""
+def rank_inner_product(a, b, n_block=1, use_accelerator=True):
+    """rank-local <a,b>; the caller does the global sum (lib/gpt/core/transform.py:91-98)"""
     a, b = eval(a), eval(b)
-    return builtins.complex(cgpt.lattice_rank_inner_product([a.obj], [b.obj])[0, 0])
+    return builtins.complex(cgpt.lattice_rank_inner_product([a], [b], 1, 1)[0, 0])
 
 
 def inner_product_norm2(a, b):
@@ -600,7 +628,7 @@ def separate(x, dimension=0):
         x = eval(x)
     grid4 = x.grid.removed_dimension(0)
     out = [lattice(grid4, x.otype) for _ in range(x.grid.fdimensions[0])]
-    cgpt.lattice_pack_rhs(x.obj, [o.obj for o in out], unpack=True)
+    capi.lattice_pack_rhs(x.obj, [o.obj for o in out], unpack=True)
     return out
 
 
@@ -615,7 +643,7 @@ def merge(lst, dimension=0, N=-1):
     for i in range(0, len(lst), N):
         grid5 = lst[i].grid.inserted_dimension(0, N)
         l5 = lattice(grid5, lst[i].otype)
-        cgpt.lattice_pack_rhs(l5.obj, [y.obj for y in lst[i:i + N]])
+        capi.lattice_pack_rhs(l5.obj, [y.obj for y in lst[i:i + N]])
         out.append(l5)
     return out[0] if len(out) == 1 else out
 
@@ -628,27 +656,27 @@ def scale_per_coordinate(d, s, a, dim):
 
 
 def axpy(d, a, x, y):
-    cgpt.lattice_axpy(d.obj, a, x.obj, y.obj)
+    cgpt.lattice_axpy(d.v_obj[0], builtins.complex(a), x.v_obj[0], y.v_obj[0])
 
 
 def axpy_norm2(d, a, x, y):
-    return d.grid.globalsum(cgpt.lattice_axpy_norm2(d.obj, a, x.obj, y.obj))
+    return d.grid.globalsum(capi.lattice_axpy_norm2(d.obj, a, x.obj, y.obj))
 
 
 def linear_combination(r, basis, Qt, n_block=8):
     rr = r if isinstance(r, list) else [r]
     q = np.atleast_2d(np.asarray(Qt))
-    cgpt.linear_combination([x.obj for x in rr], [b.obj for b in basis], q)
+    cgpt.linear_combination(rr, basis, q, n_block)
     return r
 
 
 def pick_checkerboard(cb, dst, src):
-    cgpt.lattice_pick_checkerboard(cb.tag, dst.obj, src.obj)
+    cgpt.lattice_pick_checkerboard(cb.tag, src.v_obj[0], dst.v_obj[0])  # cgpt's (cb, src, dst) order, checkerboard.py:70
     return dst
 
 
 def set_checkerboard(dst, src):
-    cgpt.lattice_set_checkerboard(dst.obj, src.obj)
+    cgpt.lattice_set_checkerboard(src.v_obj[0], dst.v_obj[0])  # (src, dst), checkerboard.py:81
     return dst
 
 
@@ -657,6 +685,10 @@ _t0 = _time.time()
 
 
 def time():  # noqa: A001
+    """seconds since start-up.  Every cgpt call of the reference returns with its work done; this library enqueues, so g.time()
+    drains the stream first -- the `t0 = g.time(); ...; t1 = g.time()` idiom of the benchmarks keeps measuring the work."""
+    if capi._initialized:
+        capi.accelerator_barrier()
     return _time.time() - _t0
 
 
@@ -737,7 +769,7 @@ def slice(x, dim):  # noqa: A001  (GPT's name)
         t0 = parallel.processor_coor(parallel.rank, parallel.mpi)[3] * lt  # first global time slice of this rank's block
         acc = np.zeros(nt, dtype=np.complex128)
         for ca, cb_ in zip(x.a.columns, x.b.columns):
-            acc[t0:t0 + lt] += cgpt.lattice_slice_inner_product(cb_.obj, ca.obj, lt)
+            acc[t0:t0 + lt] += capi.lattice_slice_inner_product(cb_.obj, ca.obj, lt)
         acc = np.asarray(gr.globalsum(acc))  # ranks split in y / z hold partial sums of the same slices
         return [builtins.complex(v) for v in acc]
     raise NotImplementedError("g.slice is implemented for g.trace(a * g.adj(b)) along time")

@@ -278,6 +278,16 @@ int cgptb_delete_lattice(cgptb_lattice* l) {
 size_t cgptb_lattice_bytes(const cgptb_lattice* l) { return l->bytes(); }
 size_t cgptb_lattice_sites(const cgptb_lattice* l) { return l->sites; }
 void* cgptb_lattice_device_ptr(cgptb_lattice* l) { return l->data; }
+int cgptb_lattice_info(const cgptb_lattice* l, int dims4[4], int* Ls, int* precision, int* otype, int* cb) {
+  CGPTB_API_BEGIN
+  CGPTB_ASSERT(l);
+  for (int i = 0; i < 4; i++) dims4[i] = l->dims4[i];
+  *Ls = l->Ls;
+  *precision = l->prec;
+  *otype = l->otype;
+  *cb = l->cb;
+  CGPTB_API_END
+}
 int cgptb_lattice_get_checkerboard(const cgptb_lattice* l) { return l->cb; }
 
 int cgptb_lattice_change_checkerboard(cgptb_lattice* l, int cb) {

@@ -7,7 +7,7 @@ Linear combinations and products stay spin matrices (0.5 * (g.gamma["I"] + g.gam
 """
 import numpy as np
 
-from gpt_b200 import cgpt
+from gpt_b200 import capi
 from gpt_b200.core import matrix_operator
 
 _BASIS = {
@@ -27,7 +27,7 @@ class spin_matrix(matrix_operator):
         m0 = self.matrix
 
         def apply(mat):
-            return lambda dst, src: cgpt.lattice_spin_matrix(dst.obj, src.obj, mat)
+            return lambda dst, src: capi.lattice_spin_matrix(dst.obj, src.obj, mat)
 
         try:
             minv = np.linalg.inv(m0)

@@ -15,7 +15,7 @@ import socket
 import numpy as np
 
 import gpt_b200 as g
-from gpt_b200 import cgpt
+from gpt_b200 import capi
 from gpt_b200.params import params_convention
 
 _FLOAT = {
@@ -82,12 +82,12 @@ def load(filename, precision=None):
     raw = np.fromfile(filename, dtype=np.uint8, offset=offset)
     grid = g.grid(dims, precision)
     U = [g.mcolor(grid) for mu in range(4)]
-    cs = cgpt.nersc_munge(raw, float_size, big, rows, [u.obj for u in U])
+    cs = capi.nersc_munge(raw, float_size, big, rows, [u.obj for u in U])
     cs_exp = int(md["CHECKSUM"].upper(), 16)
     if cs != cs_exp:
         raise RuntimeError(f"{filename}: checksum {cs:X}, header says {cs_exp:X}")
     # also check plaquette and link trace (nersc_io.py:226-247)
-    P, L = cgpt.gauge_plaquette([u.obj for u in U])
+    P, L = capi.gauge_plaquette([u.obj for u in U])
     if abs(P - float(md["PLAQUETTE"])) >= _tolerance(md["PLAQUETTE"], precision.eps):
         raise RuntimeError(f"{filename}: plaquette {P}, header says {md['PLAQUETTE']}")
     if abs(L - float(md["LINK_TRACE"])) >= _tolerance(md["LINK_TRACE"], precision.eps):
@@ -103,7 +103,7 @@ def save(filename, U, fmt=None):
     assert len(U) == 4
     grid = U[0].grid
     assert grid.precision is g.double, "single-precision configurations are not written (nersc_io.py:272-274)"
-    P, L = cgpt.gauge_plaquette([u.obj for u in U])
+    P, L = capi.gauge_plaquette([u.obj for u in U])
     # [site][mu][3][3] in native order for the checksum, big endian on disk
     data = np.stack([np.asarray(u[:]).reshape(-1, 3, 3) for u in U], axis=1).astype(np.complex128)
     cs = int(np.frombuffer(data.tobytes(), dtype="<u4").sum(dtype=np.uint64) & 0xFFFFFFFF)

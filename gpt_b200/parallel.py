@@ -6,7 +6,7 @@ libcgpt_b200 (gpt_b200/csrc/comm.cu, halo.cu).
 """
 import numpy as np
 
-from gpt_b200 import cgpt
+from gpt_b200 import capi
 
 mpi = [1, 1, 1, 1]
 rank = 0
@@ -54,9 +54,9 @@ def setup(dist, mpi_=None):
     world = dist.get_world_size()
     mpi = list(mpi_) if mpi_ is not None else default_mpi(world)
     assert int(np.prod(mpi)) == world
-    obj = [cgpt.comm_unique_id() if rank == 0 else None]
+    obj = [capi.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(obj, src=0)
-    cgpt.comm_init(rank, world, mpi, obj[0])
+    capi.comm_init(rank, world, mpi, obj[0])
     active = world > 1
 
 
@@ -64,12 +64,12 @@ def globalsum(x):
     if not active:
         return x
     if isinstance(x, complex):
-        r = cgpt.comm_globalsum([x.real, x.imag])
+        r = capi.comm_globalsum([x.real, x.imag])
         return complex(r[0], r[1])
     if isinstance(x, (float, int)):
-        return float(cgpt.comm_globalsum([float(x)])[0])
+        return float(capi.comm_globalsum([float(x)])[0])
     a = np.asarray(x)
     if np.iscomplexobj(a):
-        r = cgpt.comm_globalsum(a.astype(np.complex128).view(np.float64))
+        r = capi.comm_globalsum(a.astype(np.complex128).view(np.float64))
         return r.view(np.complex128).reshape(a.shape)
-    return cgpt.comm_globalsum(a.astype(np.float64)).reshape(a.shape)
+    return capi.comm_globalsum(a.astype(np.float64)).reshape(a.shape)

@@ -7,7 +7,8 @@ Mirrors lib/gpt/qcd/fermion/operator/{base,fine_operator,interface}.py of the re
                                              propagator, even_odd_sites_decomposed)
 """
 import gpt_b200 as g
-from gpt_b200 import cgpt
+import cgpt
+from gpt_b200 import capi
 from gpt_b200.qcd.fermion.register import register
 
 operator_tag = {}
@@ -54,12 +55,12 @@ class interface:
         """o, i: C-contiguous numpy arrays (or anything exposing __array_interface__ / data_ptr) holding full fields in
         GPT order; equivalent to  lattice[:] = i ; apply ; o[:] = lattice[:]  with the copies overlapped"""
         assert self.obj is not None
-        return cgpt.apply_fermion_operator_host(self.obj, opcode, _address(i), _address(o), _nbytes(i))
+        return capi.apply_fermion_operator_host(self.obj, opcode, _address(i), _address(o), _nbytes(i))
 
     def apply_unary_operator(self, opcode, o, i):
         assert self.obj is not None
         # cgpt adopts Grid's (in, out) order (interface.py:88-91)
-        return cgpt.apply_fermion_operator(self.obj, opcode, i.obj, o.obj)
+        return cgpt.apply_fermion_operator(self.obj, opcode, i.v_obj, o.v_obj)
 
 
 def _address(a):
@@ -95,7 +96,10 @@ class fine_operator(g.matrix_operator):
             self.F_grid = self.U_grid.inserted_dimension(0, params["Ls"])
             self.F_grid_eo = g.grid(self.F_grid.fdimensions, self.U_grid.precision, g.redblack)
 
-        self.params = {"U": [u.obj for u in U]}
+        # the grid handles travel with the parameters like in the reference (operator/base.py:65-76): they make the handle-cache
+        # tag of interface.py grid specific
+        self.params = {"U_grid": self.U_grid.obj, "U_grid_rb": self.U_grid_eo.obj, "F_grid": self.F_grid.obj,
+                       "F_grid_rb": self.F_grid_eo.obj, "U": [u.obj for u in U]}
         for k in params:
             assert k not in ["U_grid", "U_grid_rb", "F_grid", "F_grid_rb", "U"]
             self.params[k] = params[k]
@@ -144,7 +148,8 @@ class fine_operator(g.matrix_operator):
         self.Dhop = OP(mo(mat=registry.Dhop, adj_mat=registry.DhopDag, vector_space=self.vector_space_F))
         # host-buffer variant of Dhop: op.Dhop_host(dst_array, src_array)
         code = 3001 if not daggered else 4001
-        self.Dhop_host = lambda dst, src: self.interface.apply_unary_operator_host(code, dst, src)
+        iface = self.interface  # not `self`: the operator must not hold a reference to itself (fermion_operators.py:866-872)
+        self.Dhop_host = lambda dst, src: iface.apply_unary_operator_host(code, dst, src)
 
     # -- variations (base.py:222-262)
     def modified(self, **params):
@@ -215,3 +220,18 @@ class fine_operator(g.matrix_operator):
                 g.set_checkerboard(full_field, half)
 
         return even_odd_sites()
+
+
+# g.qcd.fermion.operator.base.base (lib/gpt/qcd/fermion/operator/base.py): the class user code tests operators against
+import types as _types  # noqa: E402
+
+base = _types.SimpleNamespace(base=fine_operator)
+
+
+class differentiable_fine_operator(fine_operator):
+    """operators with projected-gradient (MDeriv...) entry points (lib/gpt/qcd/fermion/operator/differentiable_fine_operator.py): the
+    force terms of HMC are outside the hot path, no operator of this package is an instance"""
+
+
+class gauge_independent_g5_hermitian:
+    """marker class of lib/gpt/qcd/fermion/operator/fine_operator.py (G5 hermiticity of Wilson-type operators)"""

@@ -3,7 +3,8 @@
 import numpy as np
 
 import gpt_b200 as g
-from gpt_b200 import cgpt
+import cgpt
+from gpt_b200 import capi
 from gpt_b200.params import params_convention
 
 
@@ -29,9 +30,9 @@ class random:
                 self.sample(x, p)
             return t
         if t is None:
-            return cgpt.random_sample_scalar(self.obj, p)
+            return cgpt.random_sample(self.obj, p)
         if isinstance(t, g.lattice):
-            cgpt.random_sample(self.obj, t.grid.serial, t.obj, p)
+            cgpt.random_sample(self.obj, {**p, **{"lattices": [t]}})
             return t
         raise TypeError(f"cannot sample into {type(t)}")
 
@@ -68,7 +69,7 @@ class random:
         """four SU(3) link lattices exp(i scale sum_a u_a T_a), u_a uniform in [-1/2, 1/2): what random.element() gives for
         the colour matrices of g.qcd.gauge.random (lib/gpt/core/random.py:110-148, lib/gpt/qcd/gauge/create.py:66-71)"""
         U = [g.mcolor(grid) for mu in range(4)]
-        cgpt.random_su3_links(self.obj, grid.serial, [u.obj for u in U], scale)
+        capi.random_su3_links(self.obj, grid.serial, [u.obj for u in U], scale)
         return U
 
     def host_array(self, grid, nel, p):
@@ -80,4 +81,4 @@ class random:
         gd = list(grid.fdimensions)
         coor = ([0] if grid.nd == 5 else []) + list(parallel.processor_coor(parallel.rank, parallel.mpi))
         ls = [c * n for c, n in zip(coor, ld)]
-        return cgpt.random_sample_host(self.obj, grid.serial, ld, gd, ls, nel, p)
+        return capi.random_sample_host(self.obj, grid.serial, ld, gd, ls, nel, p)

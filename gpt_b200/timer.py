@@ -13,7 +13,7 @@ g.timer -- sectioned stopwatch of GPT scripts (behaviour of lib/gpt/core/time.py
 Sections are timed on the HOST clock after a device barrier, like the reference, which synchronises inside every cgpt call:
 the library here enqueues asynchronously, so a section boundary drains the stream first.  `t += other` merges two timers.
 """
-from gpt_b200 import cgpt
+from gpt_b200 import capi
 
 
 class _section:
@@ -58,7 +58,7 @@ class timer:
         from gpt_b200.core import time
 
         try:
-            cgpt.accelerator_barrier()
+            capi.accelerator_barrier()
         except RuntimeError:
             pass  # no device yet (a timer around pure host code)
         return time()

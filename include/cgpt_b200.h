@@ -86,6 +86,9 @@ int cgptb_lattice_pack_rhs(cgptb_lattice* l5, cgptb_lattice* const* l4, int n, i
 size_t cgptb_lattice_bytes(const cgptb_lattice* l);
 size_t cgptb_lattice_sites(const cgptb_lattice* l);
 void* cgptb_lattice_device_ptr(cgptb_lattice* l);
+/* geometry of a lattice (what cgpt_Lattice_base::get_grid / to_decl expose, lib/cgpt/lib/lattice/implementation.h:50-54): lets the
+   host layer allocate "a lattice like this one" (cgpt.eval with dst = None) without tracking grids itself */
+int cgptb_lattice_info(const cgptb_lattice* l, int dims4[4], int* Ls, int* precision, int* otype, int* cb);
 /* cgpt.lattice_get_checkerboard / lattice_change_checkerboard (lattice.cc:189-210) */
 int cgptb_lattice_get_checkerboard(const cgptb_lattice* l);
 int cgptb_lattice_change_checkerboard(cgptb_lattice* l, int cb);
