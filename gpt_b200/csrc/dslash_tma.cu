@@ -5,8 +5,12 @@
 // hops of loads in flight per thread.  Here the loads are issued by one producer warp with cp.async.bulk.tensor (TMA)
 // into a shared-memory ring, completely decoupled from the arithmetic:
 //
-//   * work item = (4x4x4 tile of checkerboard sites in (x/2, y, z)) x (chunk of SC = 4 fifth-dimension slices) x (range
-//     of TRL time slices); a persistent CTA (one per SM) walks its items and sweeps each along t;
+//   * work item = (4x4x4 tile of checkerboard sites in (x/2, y, z)) x (group of G chunks of SC = 4 fifth-dimension slices) x
+//     (range of time slices); a persistent CTA (one per SM) walks its items and sweeps each along t.  A time step consists of
+//     G sub-steps, one per chunk, that share the tile's links: with G = 3 at Ls = 12 a CTA owns ALL fifth-dimension slices of
+//     its tile, so the 8 links of a 4d site come from L2 once instead of three times (4.8 -> 3.5 GB of L2->SM traffic per
+//     launch), 148 instead of 49 tiles are swept concurrently (the z faces between two "rounds" of CTAs are what misses in L2:
+//     5.2 -> 1.7 rounds), and everything a fifth-dimension epilogue needs is in one CTA;
 //   * per time slice the producer loads, for each of the three 32-byte component planes, the centre box of the tile
 //     (64 sites, as bottom / middle / top z layers) and its six (x/2, y, z) faces (16 sites each) -- 27 box loads with the
 //     128-byte swizzle, each shared memory row being the 4 x 32 B of one site -- plus the tile's 64 x 8 links (two boxes
@@ -15,9 +19,10 @@
 //     and after the last hop of a step) and refilled in two halves: every byte is requested 1.5 steps ahead of its use;
 //   * the +-t neighbours never travel twice: the thread that owns (site, s) reads its own entry of the centre box once
 //     per slice, uses it for the forward-t hop of the output one slice back (kept open in registers with its U_t) and
-//     carries it to the backward-t hop of the next slice;
-//   * 256 compute threads = 64 sites x 4 s; a neighbour spinor is six conflict-free LDS.128 at (slot base + per-thread
-//     constant + immediate), the site's links are broadcast LDS.128; arithmetic is the packed FFMA2 code of packed.cuh.
+//     carries its (1 +- gamma_t) projection (a half spinor) to the backward-t hop of the next slice;
+//   * 256 compute threads = 64 sites x 4 s, each with the open accumulator + carried half spinor of its G chunks in
+//     registers; a neighbour spinor is six conflict-free LDS.128 at (slot base + per-thread constant + immediate), the
+//     site's links are broadcast LDS.128; arithmetic is the packed FFMA2 code of packed.cuh.
 //
 // Reference semantics: Grid's DhopEO/DhopOE behind cgpt opcodes 3002/4002 (lib/cgpt/lib/operators/register.h:2-20),
 // restated in lib/gpt/qcd/fermion/reference/wilson_clover.py:182-200.
@@ -40,7 +45,8 @@ constexpr int TX = 4, TY = 4, TZ = 4;  // tile in checkerboard coordinates (x/2,
 constexpr int SC = 4;                  // fifth-dimension slices per chunk (4 x 32 B = one 128-byte swizzle row)
 constexpr int NS = TX * TY * TZ;       // 64 sites per time slice
 constexpr int NCOMP = NS * SC;         // compute threads
-constexpr int NTHREADS = NCOMP + 32;   // + producer warp
+constexpr int NTHREADS = NCOMP + 128;  // + producer warp group (one warp works; setmaxnreg hands its registers to the consumers)
+constexpr int REGS_PRODUCER = 40, REGS_CONSUMER = 232;  // 128 x 40 + 256 x 232 = 64512 <= 65536
 constexpr int ROW_B = 128;
 // one component plane of a slice slot: centre rows [z][y][x], then the six faces (16 rows each)
 constexpr int OFF_C = 0, OFF_XM = 8192, OFF_XP = 10240, OFF_YM = 12288, OFF_YP = 14336, OFF_ZM = 16384, OFF_ZP = 18432;
@@ -55,31 +61,34 @@ constexpr int LINK_ROW_B = LINK_ROW_F * 4;    // 304
 constexpr int LINK_HALF_B = NS * LINK_ROW_B;  // 19456
 constexpr int HALF_B = FACE_B + LINK_HALF_B;  // 37888: bytes signalled on full_A / full_B of a full step
 constexpr int NSLOT = 2;
-constexpr int STAGE_B = SLOT_B + 2 * LINK_HALF_B;  // 100352
-// barriers per slot: full_C (centre), full_A, full_B, empty_A, empty_B
+// shared memory: two spinor slots (one per sub-step in flight), two link buffers (one per time step in flight, halves A | B)
+constexpr int OFF_LINKS = NSLOT * SLOT_B;                    // 122880
+constexpr int LINKBUF_B = 2 * LINK_HALF_B;                   // 38912
+constexpr int OFF_BARS = OFF_LINKS + NSLOT * LINKBUF_B;      // 200704
+// barriers per spinor slot: full_C (centre), full_A, full_B (faces of the first / second half), empty_A, empty_B;
+// per link buffer: full_A, full_B, empty_A, empty_B
 constexpr int BAR_FC = 0, BAR_FA = 1, BAR_FB = 2, BAR_EA = 3, BAR_EB = 4, NBAR = 5;
-constexpr int SMEM_B = NSLOT * STAGE_B + NSLOT * NBAR * 8 + 1024;  // + alignment slack
+constexpr int LBAR_FA = 0, LBAR_FB = 1, LBAR_EA = 2, LBAR_EB = 3, NLBAR = 4;
+constexpr int SMEM_B = OFF_BARS + NSLOT * (NBAR + NLBAR) * 8 + 1024;  // + alignment slack
+constexpr int GMAX = 3;  // chunks per CTA (register budget: G x 36 registers of open state per thread)
 
-// One unit of work: a tile x a chunk of the fifth dimension x a range of time slices.  The host lays the items out so that
-// item i runs on CTA i % gridDim.x ("rounds" of gridDim.x concurrent items that walk t in lock-step, see build_schedule).
+// One unit of work: a tile x a group of G chunks of the fifth dimension x a range of time slices.  The host lays the items out
+// so that item i runs on CTA i % gridDim.x ("rounds" of gridDim.x concurrent items that walk t in lock-step, see build_schedule).
 struct __align__(16) ItemDesc {
-  int c, xh0, y0, z0;   // chunk index, tile origin
+  int c, xh0, y0, z0;   // group index (chunks c*G .. c*G + G - 1), tile origin
   int t0, trl;          // first output time slice, number of output time slices
-  int flags;            // L2 hints for the tile's z sides (KEEP_* / LAST_*), see build_schedule
-  int pad;
+  int pad0, pad1;
 };
-enum { KEEP_TOP = 1, KEEP_BOTTOM = 2, LAST_TOP = 4, LAST_BOTTOM = 8 };
 
 struct Geo {
   int hx, Ly, Lz, T;
-  int nbx, nby, nbz, nchunk;
+  int nbx, nby, nbz, ngroup;
   int nitems;
   int tp;  // component-plane stride of the input field in units of time slices
   int p_out;
   int ls;
   int comm_mask;  // split directions (bit 2: z, bit 3: t): hops that leave the local volume are left to the halo kernels
   int skip;  // debug (CGPTB_TMA_SKIP): bit 0 x faces, 1 y faces, 2 z faces, 3 links are not loaded (traffic attribution)
-  int hint;  // 0: no L2 hints; 1: z-boundary layers and z faces evict_last; 2: additionally everything else evict_first
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -118,16 +127,6 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
-__device__ __forceinline__ void tma_load_5d_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3,
-                                                 int c4, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(policy)
-      : "memory");
-}
-// L2 eviction priorities (createpolicy.fractional encodings, the constants CUTLASS uses for TMA cache hints)
-constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull, L2_EVICT_FIRST = 0x12F0000000000000ull, L2_EVICT_LAST = 0x14F0000000000000ull;
-
 // spinor of one (site, s) from a slice slot: a = byte address of the low 16-byte chunk of plane 0 (swizzle applied)
 __device__ __forceinline__ void lds_spinor(uint32_t a, c32 (&p)[12]) {
   const uint32_t b = a ^ 16u;
@@ -162,18 +161,23 @@ __device__ __forceinline__ void lds_link(uint32_t row, float (&wr)[9], float (&w
   }
 }
 
-// acc += recon( W(^dag) proj psi ), same arithmetic as hop_core of dslash_f32.cu
-// INIT: acc = ... instead of acc += ... (first hop of a site: saves clearing the accumulator)
-template <int MU, bool FWD, bool DAG, bool INIT = false>
-__device__ __forceinline__ void hop_math(c32 (&acc)[12], const c32 (&psi)[12], const float (&wr)[9], const float (&wi)[9]) {
+// acc += recon( W(^dag) proj psi ), same arithmetic as hop_core of dslash_f32.cu, in two pieces: the spin projection (the
+// backward-t hop carries the projected half spinor from one time slice to the next) and SU(3) x half spinor + reconstruction
+template <int MU, bool FWD, bool DAG>
+__device__ __forceinline__ void hop_proj(c32 (&h)[6], const c32 (&psi)[12]) {
   const int SGN = (FWD != DAG) ? -1 : +1;
   typedef Proj<MU, SGN> P;
-  c32 h[6];
 #pragma unroll
   for (int c = 0; c < 3; c++) {
     h[c] = add2(psi[c], times_iph<P::A>(psi[P::J0 * 3 + c]));
     h[3 + c] = add2(psi[3 + c], times_iph<P::B>(psi[P::J1 * 3 + c]));
   }
+}
+// INIT: acc = ... instead of acc += ... (first hop of a site: saves clearing the accumulator)
+template <int MU, bool FWD, bool DAG, bool INIT = false>
+__device__ __forceinline__ void hop_mulrecon(c32 (&acc)[12], const c32 (&h)[6], const float (&wr)[9], const float (&wi)[9]) {
+  const int SGN = (FWD != DAG) ? -1 : +1;
+  typedef Proj<MU, SGN> P;
   c32 chi[6];
 #pragma unroll
   for (int sp = 0; sp < 2; sp++) {
@@ -200,6 +204,12 @@ __device__ __forceinline__ void hop_math(c32 (&acc)[12], const c32 (&psi)[12], c
     acc[9 + c] = add2(INIT ? 0ull : acc[9 + c], times_iph<P::C3>(chi[P::K3 * 3 + c]));
   }
 }
+template <int MU, bool FWD, bool DAG>
+__device__ __forceinline__ void hop_math(c32 (&acc)[12], const c32 (&psi)[12], const float (&wr)[9], const float (&wi)[9]) {
+  c32 h[6];
+  hop_proj<MU, FWD, DAG>(h, psi);
+  hop_mulrecon<MU, FWD, DAG>(acc, h, wr, wi);
+}
 
 template <int MU, bool FWD, bool DAG, int D>
 __device__ __forceinline__ void hop_smem(c32 (&acc)[12], uint32_t spinor_addr, uint32_t link_row) {
@@ -214,143 +224,144 @@ __device__ __forceinline__ void hop_smem(c32 (&acc)[12], uint32_t spinor_addr, u
 // 2 memory only (all loads and stores, no hop arithmetic)
 // COMM: the lattice is split across GPUs in z and/or t (Geo::comm_mask); off-rank hops are skipped here and added by
 // k_exterior (halo.cu) once the faces have arrived
-template <bool DAG, int ABL, bool COMM>
+// G: chunks of the fifth dimension per CTA (sub-steps per time step)
+template <bool DAG, int ABL, bool COMM, int G>
 __global__ void __launch_bounds__(NTHREADS, 1)
     k_dhop_f32_tma(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                    const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmM,
-                   const __grid_constant__ CUtensorMap tmL, const Geo G, const ItemDesc* __restrict__ items,
+                   const __grid_constant__ CUtensorMap tmL, const Geo geo, const ItemDesc* __restrict__ items,
                    float* __restrict__ out, size_t out_stride) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t s_bar = sbase + NSLOT * STAGE_B;
+  const uint32_t s_bar = sbase + OFF_BARS, s_lbar = s_bar + NSLOT * NBAR * 8;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     for (int i = 0; i < NSLOT; i++) {
-      const uint32_t b = s_bar + 8 * NBAR * i;
+      const uint32_t b = s_bar + 8 * NBAR * i, lb = s_lbar + 8 * NLBAR * i;
       mbar_init(b + 8 * BAR_FC, 1);
       mbar_init(b + 8 * BAR_FA, 1);
       mbar_init(b + 8 * BAR_FB, 1);
       mbar_init(b + 8 * BAR_EA, NCOMP / 32);
       mbar_init(b + 8 * BAR_EB, NCOMP / 32);
+      mbar_init(lb + 8 * LBAR_FA, 1);
+      mbar_init(lb + 8 * LBAR_FB, 1);
+      mbar_init(lb + 8 * LBAR_EA, NCOMP / 32);
+      mbar_init(lb + 8 * LBAR_EB, NCOMP / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  if (warp == NCOMP / 32) {
+  if (warp >= NCOMP / 32) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER));
+    if (warp != NCOMP / 32) return;
     // ---------------- producer: one elected lane -------------------------------------------------------------
-    // Each slot is refilled in two halves: A = faces x-, x+, y+ and links {t-, x+, x-, y+} as soon as the consumers are
-    // past the fourth hop of the step that used the slot, then the centre box and B = faces y-, z-, z+ and links
-    // {y-, z+, z-, t+} when the step is over.  Every byte is therefore requested 1.5 steps before it is needed although
-    // only two slots fit into shared memory.
+    // Each spinor slot is refilled in two halves: A = faces x-, x+, y+ as soon as the consumers are past the fourth hop of
+    // the sub-step that used the slot, then the centre box and B = faces y-, z-, z+ when the sub-step is over; the link
+    // buffer of a time step likewise (A = {t-, x+, x-, y+} after the fourth hop of the step's last sub-step, B = {y-, z+,
+    // z-, t+} at its end).  Every spinor byte is requested 1.5 sub-steps, every link 1 + 1/(2G) steps before it is needed,
+    // although only two slots fit into shared memory.  (L2 eviction-priority hints on the z faces were measured in round 1
+    // and 2: no effect on the DRAM traffic; removed.)
     if (lane != 0) return;
-    // optional L2 eviction priorities (CGPTB_TMA_HINT): the z faces of a tile are the z-boundary layers of the tiles above and
-    // below, which are swept one "round" of CTAs earlier or later.  Measured on B200: evict_last on these lines does not
-    // change the DRAM traffic (2.47 vs 2.50 GB read per launch) and evict_first on the rest hurts (2.95 GB): default off.
-    //
-    // CGPTB_TMA_HINT >= 3, per item (ItemDesc::flags): only the z sides of a tile that face a tile of the NEXT round keep
-    // their lines (the top layer of the centre box, mode 4; and the z face beyond it, which is the next round's bottom layer,
-    // mode 3), and the round that consumes them reads them with evict_first, so at most two (x,y) planes x T stay resident.
-    uint32_t g = 0;
-    for (int item = blockIdx.x; item < G.nitems; item += gridDim.x) {
+    uint32_t g = 0, q = 0;  // sub-steps, full time steps so far
+    for (int item = blockIdx.x; item < geo.nitems; item += gridDim.x) {
       const ItemDesc it = items[item];
-      const int s0f = it.c * SC * 8;
-      uint64_t pol_rest = G.hint == 2 ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
-      uint64_t pol_ctop = (G.hint == 1 || G.hint == 2) ? L2_EVICT_LAST : L2_EVICT_NORMAL, pol_cbot = pol_ctop, pol_zp = pol_ctop,
-               pol_zm = pol_ctop;
-      if (G.hint >= 3) {
-        if (it.flags & KEEP_TOP) {
-          pol_ctop = L2_EVICT_LAST;
-          if (G.hint == 3) pol_zp = L2_EVICT_LAST;
-        }
-        if (it.flags & KEEP_BOTTOM) {
-          pol_cbot = L2_EVICT_LAST;
-          if (G.hint == 3) pol_zm = L2_EVICT_LAST;
-        }
-        if (it.flags & LAST_BOTTOM) {
-          pol_zm = L2_EVICT_FIRST;
-          if (G.hint == 3) pol_cbot = L2_EVICT_FIRST;
-        }
-        if (it.flags & LAST_TOP) {
-          pol_zp = L2_EVICT_FIRST;
-          if (G.hint == 3) pol_ctop = L2_EVICT_FIRST;
-        }
-      }
-      const int xm = (it.xh0 == 0 ? G.hx : it.xh0) - 1, xp = it.xh0 + TX == G.hx ? 0 : it.xh0 + TX;
-      const int ym = (it.y0 == 0 ? G.Ly : it.y0) - 1, yp = it.y0 + TY == G.Ly ? 0 : it.y0 + TY;
-      const int zm = (it.z0 == 0 ? G.Lz : it.z0) - 1, zp = it.z0 + TZ == G.Lz ? 0 : it.z0 + TZ;
-      for (int st = 0; st <= it.trl + 1; st++, g++) {
+      const int xm = (it.xh0 == 0 ? geo.hx : it.xh0) - 1, xp = it.xh0 + TX == geo.hx ? 0 : it.xh0 + TX;
+      const int ym = (it.y0 == 0 ? geo.Ly : it.y0) - 1, yp = it.y0 + TY == geo.Ly ? 0 : it.y0 + TY;
+      const int zm = (it.z0 == 0 ? geo.Lz : it.z0) - 1, zp = it.z0 + TZ == geo.Lz ? 0 : it.z0 + TZ;
+      const uint32_t face1 = 3 * (NS / TX) * ROW_B;  // one face, three planes
+      const uint32_t bytesA = ((geo.skip & 1) ? 0 : 2 * face1) + ((geo.skip & 2) ? 0 : face1);
+      const uint32_t bytesB = ((geo.skip & 4) ? 0 : 2 * face1) + ((geo.skip & 2) ? 0 : face1);
+      const bool load_links = ABL != 1 && !(geo.skip & 8);
+      for (int st = 0; st <= it.trl + 1; st++) {
         int tau = it.t0 - 1 + st;
-        if (tau < 0) tau += G.T;
-        if (tau >= G.T) tau -= G.T;
+        if (tau < 0) tau += geo.T;
+        if (tau >= geo.T) tau -= geo.T;
         const bool full_step = st >= 1 && st <= it.trl;
-        const uint32_t slot = g & 1u, ph = (g >> 1) & 1u;
-        const uint32_t bar = s_bar + 8 * NBAR * slot;
-        const uint32_t dst = sbase + slot * STAGE_B;
-        const uint32_t dlink = dst + SLOT_B;
-        // half A
-        mbar_wait(bar + 8 * BAR_EA, ph ^ 1u);
-        const uint32_t face1 = 3 * (NS / TX) * ROW_B;  // one face, three planes
-        const uint32_t bytesA = ((G.skip & 8) ? 0 : LINK_HALF_B) + ((G.skip & 1) ? 0 : 2 * face1) + ((G.skip & 2) ? 0 : face1);
-        const uint32_t bytesB = ((G.skip & 8) ? 0 : LINK_HALF_B) + ((G.skip & 4) ? 0 : 2 * face1) + ((G.skip & 2) ? 0 : face1);
-        if (ABL == 1 || !full_step || bytesA == 0) {
-          mbar_arrive(bar + 8 * BAR_FA);
-        } else {
-          mbar_expect_tx(bar + 8 * BAR_FA, bytesA);
-          if (!(G.skip & 8)) tma_load_5d_hint(dlink, &tmL, bar + 8 * BAR_FA, 0, it.xh0, it.y0, it.z0, tau, L2_EVICT_NORMAL);
-#pragma unroll
-          for (int k = 0; k < 3; k++) {
-            const int tq = k * G.tp + tau;
-            const uint32_t d = dst + k * PLANE_B;
-            if (!(G.skip & 1)) {
-              tma_load_5d_hint(d + OFF_XP, &tmX, bar + 8 * BAR_FA, s0f, xp, it.y0, it.z0, tq, pol_rest);
-              tma_load_5d_hint(d + OFF_XM, &tmX, bar + 8 * BAR_FA, s0f, xm, it.y0, it.z0, tq, pol_rest);
+        const uint32_t lbar = s_lbar + 8 * NLBAR * (q & 1u), lph = (q >> 1) & 1u;
+        const uint32_t dlink = sbase + OFF_LINKS + (q & 1u) * LINKBUF_B;
+        for (int c = 0; c < G; c++, g++) {
+          const int s0f = (it.c * G + c) * SC * 8;
+          const uint32_t slot = g & 1u, ph = (g >> 1) & 1u;
+          const uint32_t bar = s_bar + 8 * NBAR * slot;
+          const uint32_t dst = sbase + slot * SLOT_B;
+          // half A
+          if (c == 0 && full_step) {
+            mbar_wait(lbar + 8 * LBAR_EA, lph ^ 1u);
+            if (load_links) {
+              mbar_expect_tx(lbar + 8 * LBAR_FA, (uint32_t)LINK_HALF_B);
+              tma_load_5d(dlink, &tmL, lbar + 8 * LBAR_FA, 0, it.xh0, it.y0, it.z0, tau);
+            } else {
+              mbar_arrive(lbar + 8 * LBAR_FA);
             }
-            if (!(G.skip & 2)) tma_load_5d_hint(d + OFF_YP, &tmY, bar + 8 * BAR_FA, s0f, it.xh0, yp, it.z0, tq, pol_rest);
           }
-        }
-        // centre and half B
-        mbar_wait(bar + 8 * BAR_EB, ph ^ 1u);
-        if (ABL == 1) {
-          mbar_arrive(bar + 8 * BAR_FC);
-          mbar_arrive(bar + 8 * BAR_FB);
-        } else {
-          mbar_expect_tx(bar + 8 * BAR_FC, (uint32_t)CENTER_B);
-#pragma unroll
-          for (int k = 0; k < 3; k++) {
-            // centre box as bottom layer, two middle layers, top layer (rows [z][y][x]: 16 rows per layer)
-            const uint32_t d = dst + k * PLANE_B + OFF_C;
-            const int tq = k * G.tp + tau;
-            tma_load_5d_hint(d, &tmZ, bar + 8 * BAR_FC, s0f, it.xh0, it.y0, it.z0, tq, pol_cbot);
-            tma_load_5d_hint(d + 16 * ROW_B, &tmM, bar + 8 * BAR_FC, s0f, it.xh0, it.y0, it.z0 + 1, tq, pol_rest);
-            tma_load_5d_hint(d + 48 * ROW_B, &tmZ, bar + 8 * BAR_FC, s0f, it.xh0, it.y0, it.z0 + 3, tq, pol_ctop);
-          }
-          if (full_step && bytesB != 0) {
-            mbar_expect_tx(bar + 8 * BAR_FB, bytesB);
-            if (!(G.skip & 8))
-              tma_load_5d_hint(dlink + LINK_HALF_B, &tmL, bar + 8 * BAR_FB, 0, it.xh0, it.y0, it.z0, G.T + tau, L2_EVICT_NORMAL);
+          mbar_wait(bar + 8 * BAR_EA, ph ^ 1u);
+          if (ABL == 1 || !full_step || bytesA == 0) {
+            mbar_arrive(bar + 8 * BAR_FA);
+          } else {
+            mbar_expect_tx(bar + 8 * BAR_FA, bytesA);
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-              const int tq = k * G.tp + tau;
+              const int tq = k * geo.tp + tau;
               const uint32_t d = dst + k * PLANE_B;
-              if (!(G.skip & 2)) tma_load_5d_hint(d + OFF_YM, &tmY, bar + 8 * BAR_FB, s0f, it.xh0, ym, it.z0, tq, pol_rest);
-              if (!(G.skip & 4)) {
-                tma_load_5d_hint(d + OFF_ZP, &tmZ, bar + 8 * BAR_FB, s0f, it.xh0, it.y0, zp, tq, pol_zp);
-                tma_load_5d_hint(d + OFF_ZM, &tmZ, bar + 8 * BAR_FB, s0f, it.xh0, it.y0, zm, tq, pol_zm);
+              if (!(geo.skip & 1)) {
+                tma_load_5d(d + OFF_XP, &tmX, bar + 8 * BAR_FA, s0f, xp, it.y0, it.z0, tq);
+                tma_load_5d(d + OFF_XM, &tmX, bar + 8 * BAR_FA, s0f, xm, it.y0, it.z0, tq);
+              }
+              if (!(geo.skip & 2)) tma_load_5d(d + OFF_YP, &tmY, bar + 8 * BAR_FA, s0f, it.xh0, yp, it.z0, tq);
+            }
+          }
+          // centre and half B
+          mbar_wait(bar + 8 * BAR_EB, ph ^ 1u);
+          if (ABL == 1) {
+            mbar_arrive(bar + 8 * BAR_FC);
+          } else {
+            mbar_expect_tx(bar + 8 * BAR_FC, (uint32_t)CENTER_B);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+              // centre box as bottom layer, two middle layers, top layer (rows [z][y][x]: 16 rows per layer)
+              const uint32_t d = dst + k * PLANE_B + OFF_C;
+              const int tq = k * geo.tp + tau;
+              tma_load_5d(d, &tmZ, bar + 8 * BAR_FC, s0f, it.xh0, it.y0, it.z0, tq);
+              tma_load_5d(d + 16 * ROW_B, &tmM, bar + 8 * BAR_FC, s0f, it.xh0, it.y0, it.z0 + 1, tq);
+              tma_load_5d(d + 48 * ROW_B, &tmZ, bar + 8 * BAR_FC, s0f, it.xh0, it.y0, it.z0 + 3, tq);
+            }
+          }
+          if (c == 0 && full_step) {
+            mbar_wait(lbar + 8 * LBAR_EB, lph ^ 1u);
+            if (load_links) {
+              mbar_expect_tx(lbar + 8 * LBAR_FB, (uint32_t)LINK_HALF_B);
+              tma_load_5d(dlink + LINK_HALF_B, &tmL, lbar + 8 * LBAR_FB, 0, it.xh0, it.y0, it.z0, geo.T + tau);
+            } else {
+              mbar_arrive(lbar + 8 * LBAR_FB);
+            }
+          }
+          if (ABL == 1 || !full_step || bytesB == 0) {
+            mbar_arrive(bar + 8 * BAR_FB);
+          } else {
+            mbar_expect_tx(bar + 8 * BAR_FB, bytesB);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+              const int tq = k * geo.tp + tau;
+              const uint32_t d = dst + k * PLANE_B;
+              if (!(geo.skip & 2)) tma_load_5d(d + OFF_YM, &tmY, bar + 8 * BAR_FB, s0f, it.xh0, ym, it.z0, tq);
+              if (!(geo.skip & 4)) {
+                tma_load_5d(d + OFF_ZP, &tmZ, bar + 8 * BAR_FB, s0f, it.xh0, it.y0, zp, tq);
+                tma_load_5d(d + OFF_ZM, &tmZ, bar + 8 * BAR_FB, s0f, it.xh0, it.y0, zm, tq);
               }
             }
-          } else {
-            mbar_arrive(bar + 8 * BAR_FB);
           }
         }
+        if (full_step) q++;
       }
     }
     return;
   }
 
-  // ---------------- consumers: thread = (site l of the tile, slice j of the chunk) -------------------------
+  // ---------------- consumers: thread = (site l of the tile, slice j of each of the G chunks) -------------
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_CONSUMER));
   const int l = tid >> 2, j = tid & 3;
   const int lx = l & 3, ly = (l >> 2) & 3, lz = l >> 4;
   auto rowaddr = [&](int buf, int row) -> uint32_t { return (uint32_t)(buf + row * ROW_B + (((2 * j) ^ (row & 7)) << 4)); };
@@ -361,82 +372,103 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   const uint32_t a_ym = ly > 0 ? rowaddr(OFF_C, l - TX) : rowaddr(OFF_YM, lz * TX + lx);
   const uint32_t a_zp = lz < TZ - 1 ? rowaddr(OFF_C, l + TX * TY) : rowaddr(OFF_ZP, ly * TX + lx);
   const uint32_t a_zm = lz > 0 ? rowaddr(OFF_C, l - TX * TY) : rowaddr(OFF_ZM, ly * TX + lx);
-  const int b0 = (ly + lz + G.p_out) & 1;  // tile origins are even
-  const int slice_sites = G.hx * G.Ly * G.Lz;
+  const int b0 = (ly + lz + geo.p_out) & 1;  // tile origins are even
+  const int slice_sites = geo.hx * geo.Ly * geo.Lz;
 
-  c32 acc[12], carry[12];
+  // open state per chunk: the accumulator of the previous slice's output (waits for its forward-t hop) and the
+  // (1 +- gamma_t) projection of the previous slice's own spinor (for the backward-t hop of this slice's output)
+  c32 acc[G][12], hc[G][6];
   float utr[9], uti[9];
 #pragma unroll
-  for (int k = 0; k < 12; k++) acc[k] = carry[k] = 0ull;
+  for (int c = 0; c < G; c++) {
+#pragma unroll
+    for (int k = 0; k < 12; k++) acc[c][k] = 0ull;
+#pragma unroll
+    for (int k = 0; k < 6; k++) hc[c][k] = 0ull;
+  }
 #pragma unroll
   for (int k = 0; k < 9; k++) utr[k] = uti[k] = 0.f;
 
-  uint32_t g = 0;
-  for (int item = blockIdx.x; item < G.nitems; item += gridDim.x) {
+  uint32_t g = 0, q = 0;
+  for (int item = blockIdx.x; item < geo.nitems; item += gridDim.x) {
     const ItemDesc it = items[item];
-    const int site0 = (it.xh0 + lx) + G.hx * ((it.y0 + ly) + G.Ly * (it.z0 + lz));
-    const int s = it.c * SC + j;
+    const int site0 = (it.xh0 + lx) + geo.hx * ((it.y0 + ly) + geo.Ly * (it.z0 + lz));
     int tau_prev = 0;
-    for (int st = 0; st <= it.trl + 1; st++, g++) {
+    for (int st = 0; st <= it.trl + 1; st++) {
       int tau = it.t0 - 1 + st;
-      if (tau < 0) tau += G.T;
-      if (tau >= G.T) tau -= G.T;
+      if (tau < 0) tau += geo.T;
+      if (tau >= geo.T) tau -= geo.T;
       const bool full_step = st >= 1 && st <= it.trl;
-      const uint32_t slot = g & 1u, ph = (g >> 1) & 1u;
-      const uint32_t bar = s_bar + 8 * NBAR * slot;
-      const uint32_t sp = sbase + slot * STAGE_B;
-      const uint32_t lrowA = sp + SLOT_B + l * LINK_ROW_B, lrowB = lrowA + LINK_HALF_B;
-      mbar_wait(bar + 8 * BAR_FC, ph);
-      c32 own[12];
-      lds_spinor(sp + a_own, own);
-      if (st >= 2) {
-        // forward-t hop closes the output of the previous slice
-        if (ABL != 2 && !(COMM && (G.comm_mask & 8) && tau_prev == G.T - 1)) hop_math<3, true, DAG>(acc, own, utr, uti);
-        const size_t site = ((size_t)site0 + (size_t)slice_sites * tau_prev) * G.ls + s;
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          float v[8];
-#pragma unroll
-          for (int e = 0; e < 4; e++) upk(acc[4 * k + e], v[2 * e], v[2 * e + 1]);
-          st256_cs(out + (k * out_stride + site) * 8, v);
-        }
-      }
+      const uint32_t lbar = s_lbar + 8 * NLBAR * (q & 1u), lph = (q >> 1) & 1u;
+      const uint32_t lrowA = sbase + OFF_LINKS + (q & 1u) * LINKBUF_B + l * LINK_ROW_B, lrowB = lrowA + LINK_HALF_B;
       const int b = (b0 + tau) & 1;
       const uint32_t a_xp = b ? a_right : a_own, a_xm = b ? a_own : a_left;
-      // ---- first half: t-, x+, x-, y+
-      mbar_wait(bar + 8 * BAR_FA, ph);
-      if (ABL == 2) {
 #pragma unroll
-        for (int k = 0; k < 12; k++) acc[k] = own[k];
-      } else if (full_step) {
-        if (COMM && (G.comm_mask & 8) && tau == 0) {
+      for (int c = 0; c < G; c++, g++) {
+        const int s = (it.c * G + c) * SC + j;
+        const uint32_t slot = g & 1u, ph = (g >> 1) & 1u;
+        const uint32_t bar = s_bar + 8 * NBAR * slot;
+        const uint32_t sp = sbase + slot * SLOT_B;
+        mbar_wait(bar + 8 * BAR_FC, ph);
+        c32 own[12];
+        lds_spinor(sp + a_own, own);
+        if (st >= 2) {
+          // forward-t hop closes the output of the previous slice
+          if (ABL != 2 && !(COMM && (geo.comm_mask & 8) && tau_prev == geo.T - 1)) hop_math<3, true, DAG>(acc[c], own, utr, uti);
+          const size_t site = ((size_t)site0 + (size_t)slice_sites * tau_prev) * geo.ls + s;
 #pragma unroll
-          for (int k = 0; k < 12; k++) acc[k] = 0ull;
-        } else {
-          float wr[9], wi[9];
-          lds_link<0>(lrowA, wr, wi);
-          hop_math<3, false, DAG, true>(acc, carry, wr, wi);
+          for (int k = 0; k < 3; k++) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 4; e++) upk(acc[c][4 * k + e], v[2 * e], v[2 * e + 1]);
+            st256_cs(out + (k * out_stride + site) * 8, v);
+          }
         }
-        hop_smem<0, true, DAG, 1>(acc, sp + a_xp, lrowA);
-        hop_smem<0, false, DAG, 2>(acc, sp + a_xm, lrowA);
-        hop_smem<1, true, DAG, 3>(acc, sp + a_yp, lrowA);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar + 8 * BAR_EA);
-      // ---- second half: y-, z+, z-, and U_t for the forward-t hop of the next step
-      mbar_wait(bar + 8 * BAR_FB, ph);
-      if (ABL != 2 && full_step) {
-        hop_smem<1, false, DAG, 0>(acc, sp + a_ym, lrowB);
-        // lz is uniform within a warp (8 consecutive sites), so these branches do not diverge
-        if (!(COMM && (G.comm_mask & 4) && it.z0 + lz == G.Lz - 1)) hop_smem<2, true, DAG, 1>(acc, sp + a_zp, lrowB);
-        if (!(COMM && (G.comm_mask & 4) && it.z0 + lz == 0)) hop_smem<2, false, DAG, 2>(acc, sp + a_zm, lrowB);
-        lds_link<3>(lrowB, utr, uti);
-      }
+        // ---- first half: t-, x+, x-, y+
+        mbar_wait(bar + 8 * BAR_FA, ph);
+        if (c == 0 && full_step) mbar_wait(lbar + 8 * LBAR_FA, lph);
+        if (ABL == 2) {
 #pragma unroll
-      for (int k = 0; k < 12; k++) carry[k] = own[k];
+          for (int k = 0; k < 12; k++) acc[c][k] = own[k];
+        } else if (full_step) {
+          if (COMM && (geo.comm_mask & 8) && tau == 0) {
+#pragma unroll
+            for (int k = 0; k < 12; k++) acc[c][k] = 0ull;
+          } else {
+            float wr[9], wi[9];
+            lds_link<0>(lrowA, wr, wi);
+            hop_mulrecon<3, false, DAG, true>(acc[c], hc[c], wr, wi);
+          }
+        }
+        hop_proj<3, false, DAG>(hc[c], own);  // own is dead from here on
+        if (ABL != 2 && full_step) {
+          hop_smem<0, true, DAG, 1>(acc[c], sp + a_xp, lrowA);
+          hop_smem<0, false, DAG, 2>(acc[c], sp + a_xm, lrowA);
+          hop_smem<1, true, DAG, 3>(acc[c], sp + a_yp, lrowA);
+        }
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(bar + 8 * BAR_EA);
+          if (c == G - 1 && full_step) mbar_arrive(lbar + 8 * LBAR_EA);
+        }
+        // ---- second half: y-, z+, z-, and U_t for the forward-t hops of the next step
+        mbar_wait(bar + 8 * BAR_FB, ph);
+        if (c == 0 && full_step) mbar_wait(lbar + 8 * LBAR_FB, lph);
+        if (ABL != 2 && full_step) {
+          hop_smem<1, false, DAG, 0>(acc[c], sp + a_ym, lrowB);
+          // lz is uniform within a warp (8 consecutive sites), so these branches do not diverge
+          if (!(COMM && (geo.comm_mask & 4) && it.z0 + lz == geo.Lz - 1)) hop_smem<2, true, DAG, 1>(acc[c], sp + a_zp, lrowB);
+          if (!(COMM && (geo.comm_mask & 4) && it.z0 + lz == 0)) hop_smem<2, false, DAG, 2>(acc[c], sp + a_zm, lrowB);
+          if (c == G - 1) lds_link<3>(lrowB, utr, uti);
+        }
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(bar + 8 * BAR_EB);
+          if (c == G - 1 && full_step) mbar_arrive(lbar + 8 * LBAR_EB);
+        }
+      }
+      if (full_step) q++;
       tau_prev = tau;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar + 8 * BAR_EB);
     }
   }
 }
@@ -485,31 +517,27 @@ static int env_i(const char* name, int dflt) {
 }
 
 // Work schedule of one launch (item i runs on CTA i % grid; the CTAs of a "round" walk t in lock-step, so the x / y / z
-// neighbours inside a round's set of tiles and the three chunk-CTAs that share a tile's links hit in L2).
+// neighbours inside a round's set of tiles hit in L2).
 //
-//   sched 1 (default): every (tile, chunk) pair is swept over the WHOLE time range by one CTA -- floor(pairs / grid) full
-//     rounds --, and the pairs that are left share the last round, each split into floor(grid / left) time ranges.  Compared
-//     with fixed ranges of 16 slices (sched 0: 3072 items of 18 steps at 32^3 x 64 x 12) this drops the two extra centre
-//     loads at the ends of a range from 2/16 to ~2/64 of the centre traffic and the number of steps per CTA from 378 to 345.
-//   sched 0: the round-1 schedule, kept for A/B runs (CGPTB_TMA_SCHED=0, range length CGPTB_TMA_TRL).
-//
-// flags (CGPTB_TMA_HINT >= 3): the z sides of a tile whose z neighbour runs one round later (KEEP_*) or ran one round earlier
-// (LAST_*), see the producer.
-static std::vector<ItemDesc> build_schedule(const Geo& G, int grid, int t_begin, int t_count, int sched, int trl_max) {
+//   sched 1 (default): every (tile, chunk group) pair is swept over the WHOLE time range by one CTA -- floor(pairs / grid) full
+//     rounds --, and the pairs that are left are cut into m time ranges each, m chosen to minimise the number of time steps the
+//     left-over rounds take (ranges cost two extra centre loads each).  32^3 x 64 x 12 with G = 3: 256 pairs on 148 CTAs = one
+//     full round + 108 pairs x 4 ranges in three short rounds (116 time steps per CTA, 111 if the work were divisible).
+//   sched 0: fixed ranges of CGPTB_TMA_TRL slices for every pair (the round-1 schedule), kept for A/B runs.
+static std::vector<ItemDesc> build_schedule(const Geo& geo, int grid, int t_begin, int t_count, int sched, int trl_max) {
   std::vector<ItemDesc> items;
-  const int ntile = G.nbx * G.nby * G.nbz, npairs = ntile * G.nchunk;
+  const int ntile = geo.nbx * geo.nby * geo.nbz, npairs = ntile * geo.ngroup;
   auto make = [&](int pair, int t0, int trl) {
     ItemDesc it;
-    it.c = pair % G.nchunk;
-    int r = pair / G.nchunk;
-    it.xh0 = (r % G.nbx) * TX;
-    r /= G.nbx;
-    it.y0 = (r % G.nby) * TY;
-    it.z0 = (r / G.nby) * TZ;
+    it.c = pair % geo.ngroup;
+    int r = pair / geo.ngroup;
+    it.xh0 = (r % geo.nbx) * TX;
+    r /= geo.nbx;
+    it.y0 = (r % geo.nby) * TY;
+    it.z0 = (r / geo.nby) * TZ;
     it.t0 = t0;
     it.trl = trl;
-    it.flags = 0;
-    it.pad = 0;
+    it.pad0 = it.pad1 = 0;
     return it;
   };
   if (sched == 0) {
@@ -521,31 +549,26 @@ static std::vector<ItemDesc> build_schedule(const Geo& G, int grid, int t_begin,
     return items;
   }
   const int rounds = npairs / grid, left = npairs % grid;
-  auto round_of = [&](int pair) { return pair / grid < rounds ? pair / grid : rounds; };
-  auto with_flags = [&](ItemDesc it, int pair) {
-    if (G.nbz < 2) return it;
-    const int per_z = G.nchunk * G.nbx * G.nby, bz = pair / per_z, rm = round_of(pair);
-    const int up = round_of(pair + ((bz + 1) % G.nbz - bz) * per_z), dn = round_of(pair + ((bz + G.nbz - 1) % G.nbz - bz) * per_z);
-    if (up == rm + 1) it.flags |= KEEP_TOP;
-    if (up == rm - 1) it.flags |= LAST_TOP;
-    if (dn == rm + 1) it.flags |= KEEP_BOTTOM;
-    if (dn == rm - 1) it.flags |= LAST_BOTTOM;
-    return it;
-  };
-  for (int pair = 0; pair < rounds * grid; pair++) items.push_back(with_flags(make(pair, t_begin, t_count), pair));
+  for (int pair = 0; pair < rounds * grid; pair++) items.push_back(make(pair, t_begin, t_count));
   if (left) {
-    int k = grid / left;
-    const int kmax = t_count >= 8 ? t_count / 4 : 1;  // ranges shorter than 4 slices pay too much for their two extra loads
-    if (k > kmax) k = kmax;
-    if (k < 1) k = 1;
-    for (int q = 0; q < left; q++) {
-      const int pair = rounds * grid + q;
-      int t0 = t_begin;
-      for (int j = 0; j < k; j++) {
-        const int trl = t_count / k + (j < t_count % k ? 1 : 0);
-        items.push_back(with_flags(make(pair, t0, trl), pair));
-        t0 += trl;
+    // ranges shorter than 4 slices pay too much for their two extra loads
+    const int mmax = t_count >= 8 ? t_count / 4 : 1;
+    int m = 1;
+    double best = 1e30;
+    for (int k = 1; k <= mmax; k++) {
+      const int r = (left * k + grid - 1) / grid;
+      const double cost = r * ((t_count + k - 1) / k + 1.0);
+      if (cost < best - 1e-9) {
+        best = cost;
+        m = k;
       }
+    }
+    // range-major: the pairs of one range are spatial neighbours and run concurrently
+    int t0 = t_begin;
+    for (int j = 0; j < m; j++) {
+      const int trl = t_count / m + (j < t_count % m ? 1 : 0);
+      for (int q = 0; q < left; q++) items.push_back(make(rounds * grid + q, t0, trl));
+      t0 += trl;
     }
   }
   return items;
@@ -558,7 +581,7 @@ struct SchedKey {
 static std::map<SchedKey, std::pair<ItemDesc*, int>> g_sched;
 
 static const ItemDesc* schedule_on_device(const Geo& G, int grid, int t_begin, int t_count, int sched, int trl_max, int* nitems) {
-  SchedKey key = {{G.hx, G.Ly, G.Lz, G.T, G.nchunk, grid, t_begin, t_count, sched, trl_max, 0, 0}};
+  SchedKey key = {{G.hx, G.Ly, G.Lz, G.T, G.ngroup, grid, t_begin, t_count, sched, trl_max, G.nbx, G.nby}};
   auto f = g_sched.find(key);
   if (f == g_sched.end()) {
     std::vector<ItemDesc> items = build_schedule(G, grid, t_begin, t_count, sched, trl_max);
@@ -618,7 +641,14 @@ void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, s
   G.nbx = g.hx / TX;
   G.nby = g.L[1] / TY;
   G.nbz = g.L[2] / TZ;
-  G.nchunk = ls / SC;
+  // chunks per CTA: the largest divisor of the number of chunks that the register budget allows (CGPTB_TMA_G overrides)
+  const int nchunk = ls / SC;
+  int ng = 1;
+  for (int d = 1; d <= GMAX; d++)
+    if (nchunk % d == 0) ng = d;
+  const int ng_env = env_i("CGPTB_TMA_G", 0);
+  if (ng_env >= 1 && ng_env <= GMAX && nchunk % ng_env == 0) ng = ng_env;
+  G.ngroup = nchunk / ng;
   if (t_count <= 0) {
     t_begin = 0;
     t_count = G.T;
@@ -629,8 +659,6 @@ void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, s
   G.tp = (int)(in_stride / slice_blocks);
   G.p_out = p_out;
   G.ls = ls;
-
-  G.hint = env_i("CGPTB_TMA_HINT", 0);
   G.skip = env_i("CGPTB_TMA_SKIP", 0);
   G.comm_mask = g.comm_mask;
   // box shapes: one x column, one y row, one z layer (also the bottom / top layer of the centre box), two z layers (its middle)
@@ -655,16 +683,6 @@ void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, s
     const cuuint32_t bl[5] = {LINK_ROW_F, TX, TY, TZ, 1};
     encode5(&tmL, op->links_pad[p_out], dims, strides, bl, CU_TENSOR_MAP_SWIZZLE_NONE);
   }
-  static bool configured = false;
-  if (!configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(k_dhop_f32_tma<false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B));
-    CUDA_CHECK(cudaFuncSetAttribute(k_dhop_f32_tma<true, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B));
-    CUDA_CHECK(cudaFuncSetAttribute(k_dhop_f32_tma<false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B));
-    CUDA_CHECK(cudaFuncSetAttribute(k_dhop_f32_tma<true, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B));
-    CUDA_CHECK(cudaFuncSetAttribute(k_dhop_f32_tma<false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B));
-    CUDA_CHECK(cudaFuncSetAttribute(k_dhop_f32_tma<false, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B));
-    configured = true;
-  }
   const int grid_env = env_i("CGPTB_TMA_GRID", 0);
   // a persistent grid on every SM would keep the NCCL send/recv kernels of the halo exchange from being scheduled until
   // the stencil is done, so a split lattice leaves a few SMs free for them (CGPTB_TMA_COMM_SMS)
@@ -672,23 +690,32 @@ void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, s
   if (grid < 1) grid = 1;
   const ItemDesc* items = schedule_on_device(G, grid, t_begin, t_count, env_i("CGPTB_TMA_SCHED", 1), env_i("CGPTB_TMA_TRL", 16), &G.nitems);
   if (grid > G.nitems) grid = G.nitems;
-  const int abl = env_i("CGPTB_ABLATE", 0);
-#define TMA_LAUNCH(DAG_, ABL_, COMM_) \
-  k_dhop_f32_tma<DAG_, ABL_, COMM_><<<grid, NTHREADS, SMEM_B, g_stream>>>(tmX, tmY, tmZ, tmM, tmL, G, items, pout, out_stride)
-  if (g.comm_mask) {
-    if (dag)
-      TMA_LAUNCH(true, 0, true);
-    else
-      TMA_LAUNCH(false, 0, true);
-  } else if (abl == 1)
-    TMA_LAUNCH(false, 1, false);
-  else if (abl == 2)
-    TMA_LAUNCH(false, 2, false);
-  else if (dag)
-    TMA_LAUNCH(true, 0, false);
-  else
-    TMA_LAUNCH(false, 0, false);
-#undef TMA_LAUNCH
+  const int abl = g.comm_mask ? 0 : env_i("CGPTB_ABLATE", 0);
+  typedef void (*kernel_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const Geo,
+                           const ItemDesc*, float*, size_t);
+  kernel_t kern = 0;
+#define TMA_PICK(G_)                                                                                  \
+  if (ng == G_) {                                                                                     \
+    if (g.comm_mask)                                                                                  \
+      kern = dag ? k_dhop_f32_tma<true, 0, true, G_> : k_dhop_f32_tma<false, 0, true, G_>;            \
+    else if (abl == 1)                                                                                \
+      kern = k_dhop_f32_tma<false, 1, false, G_>;                                                     \
+    else if (abl == 2)                                                                                \
+      kern = k_dhop_f32_tma<false, 2, false, G_>;                                                     \
+    else                                                                                              \
+      kern = dag ? k_dhop_f32_tma<true, 0, false, G_> : k_dhop_f32_tma<false, 0, false, G_>;          \
+  }
+  TMA_PICK(1)
+  TMA_PICK(2)
+  TMA_PICK(3)
+#undef TMA_PICK
+  CGPTB_ASSERT(kern != 0);
+  static std::map<kernel_t, bool> configured;
+  if (!configured[kern]) {
+    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B));
+    configured[kern] = true;
+  }
+  kern<<<grid, NTHREADS, SMEM_B, g_stream>>>(tmX, tmY, tmZ, tmM, tmL, G, items, pout, out_stride);
   LAUNCH_CHECK();
 }
 

@@ -439,7 +439,7 @@ def test_dhop_host_buffers_double(g, fields):
 # TMA sweep kernel (dslash_tma.cu): asymmetric lattices, several Ls, work schedules that put many items and
 # time ranges on one CTA; against the oracle and against the L1 kernels (CGPTB_NO_TMA)
 # ---------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("dims,Ls", [([16, 8, 12, 8], 8), ([8, 12, 8, 6], 4), ([8, 8, 8, 16], 16)])
+@pytest.mark.parametrize("dims,Ls", [([16, 8, 12, 8], 8), ([8, 12, 8, 6], 4), ([8, 8, 8, 16], 16), ([8, 16, 8, 10], 12), ([8, 8, 8, 6], 24)])
 def test_tma_sweep_kernel_geometries(g, dims, Ls, monkeypatch):
     rng = oracle_random("tma" + str(dims))
     U = qcd.gauge_random(rng, dims, scale=0.8)
@@ -456,8 +456,12 @@ def test_tma_sweep_kernel_geometries(g, dims, Ls, monkeypatch):
         l1 = from_spinor(g(op * src), s5)
         monkeypatch.delenv("CGPTB_NO_TMA")
         assert rel(l1, ref) < TOL["single"]
-        for env in ({}, {"CGPTB_TMA_GRID": "1", "CGPTB_TMA_TRL": "2"}, {"CGPTB_TMA_GRID": "5", "CGPTB_TMA_TRL": "4"},
-                    {"CGPTB_TMA_GRID": "3", "CGPTB_TMA_TRL": "1"}):
+        # default: G = 3 / 2 / 1 chunks of four s-slices per CTA (the largest that divides Ls / 4); CGPTB_TMA_G forces another
+        # split, CGPTB_TMA_GRID few CTAs (many items per CTA), CGPTB_TMA_SCHED=0 fixed time ranges of CGPTB_TMA_TRL slices
+        for env in ({}, {"CGPTB_TMA_GRID": "1"}, {"CGPTB_TMA_GRID": "5", "CGPTB_TMA_G": "1"}, {"CGPTB_TMA_GRID": "7", "CGPTB_TMA_G": "2"},
+                    {"CGPTB_TMA_SCHED": "0", "CGPTB_TMA_GRID": "1", "CGPTB_TMA_TRL": "2"},
+                    {"CGPTB_TMA_SCHED": "0", "CGPTB_TMA_GRID": "5", "CGPTB_TMA_TRL": "4", "CGPTB_TMA_G": "1"},
+                    {"CGPTB_TMA_SCHED": "0", "CGPTB_TMA_GRID": "3", "CGPTB_TMA_TRL": "1"}):
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
             got = from_spinor(g(op * src), s5)
