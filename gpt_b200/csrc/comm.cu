@@ -5,8 +5,12 @@
 //
 // NCCL is resolved at run time with dlopen("libnccl.so.2") so that a single-GPU process has no NCCL
 // dependency; inside a torch process this picks up the libnccl torch already mapped.
+#include <cuda.h>
 #include <dlfcn.h>
 #include <nccl.h>
+#include <map>
+#include <string>
+#include <vector>
 #include "common.cuh"
 
 namespace cgptb {
@@ -24,6 +28,7 @@ struct NcclApi {
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = 0;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = 0;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = 0;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = 0;
 };
 static NcclApi nccl;
 
@@ -53,6 +58,7 @@ static void load_nccl() {
   SYM(Send, "ncclSend")
   SYM(Recv, "ncclRecv")
   SYM(AllReduce, "ncclAllReduce")
+  SYM(AllGather, "ncclAllGather")
 #undef SYM
 }
 
@@ -82,6 +88,113 @@ void comm_exchange_end() { NCCL_CHECK(nccl.GroupEnd()); }
 void comm_allreduce_device(double* dev, int n, cudaStream_t s) {
   if (!g_comm.active) return;
   NCCL_CHECK(nccl.AllReduce(dev, dev, n, ncclDouble, ncclSum, (ncclComm_t)g_comm.nccl, s));
+}
+
+// out = [world][bytes] in device memory, on stream s
+void comm_allgather_device(const void* in, void* out, size_t bytes, cudaStream_t s) {
+  NCCL_CHECK(nccl.AllGather(in, out, bytes, ncclUint8, (ncclComm_t)g_comm.nccl, s));
+}
+
+// every rank contributes `bytes` bytes of host memory; out = [world][bytes] (set-up paths only: synchronises the stream)
+void comm_allgather_host(const void* in, void* out, size_t bytes) {
+  unsigned char *d_in, *d_out;
+  CUDA_CHECK(cudaMalloc(&d_in, bytes));
+  CUDA_CHECK(cudaMalloc(&d_out, bytes * g_comm.world));
+  CUDA_CHECK(cudaMemcpyAsync(d_in, in, bytes, cudaMemcpyHostToDevice, g_stream));
+  NCCL_CHECK(nccl.AllGather(d_in, d_out, bytes, ncclUint8, (ncclComm_t)g_comm.nccl, g_stream));
+  CUDA_CHECK(cudaMemcpyAsync(out, d_out, bytes * g_comm.world, cudaMemcpyDeviceToHost, g_stream));
+  CUDA_CHECK(cudaStreamSynchronize(g_stream));
+  CUDA_CHECK(cudaFree(d_in));
+  CUDA_CHECK(cudaFree(d_out));
+}
+
+// ---- peer memory (CUDA IPC) and stream-ordered flags: the halo exchange without NCCL kernels -------------------------------
+// A rank exports a device allocation (comm_export), all-gathers the descriptor, and maps the neighbours' allocations
+// (comm_import; mappings are cached for the life of the process and never closed: the exporting side keeps its halo arenas
+// in a pool instead of freeing them).  cuStreamWriteValue32 / cuStreamWaitValue32 on words of such an allocation order a
+// receiver's kernels after a sender's.
+static CUresult (*p_cuStreamWriteValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = 0;
+static CUresult (*p_cuStreamWaitValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = 0;
+static CUresult (*p_cuMemGetAddressRange)(CUdeviceptr*, size_t*, CUdeviceptr) = 0;
+static int p2p_state = -1;  // -1 unknown, 0 unavailable, 1 available
+
+static bool load_memops() {
+  if (p_cuStreamWriteValue32) return true;
+  cudaDriverEntryPointQueryResult q;
+  void* f = 0;
+  if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !f) return false;
+  *(void**)(&p_cuStreamWriteValue32) = f;
+  if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !f) return false;
+  *(void**)(&p_cuStreamWaitValue32) = f;
+  if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !f) return false;
+  *(void**)(&p_cuMemGetAddressRange) = f;
+  return true;
+}
+
+void comm_export(void* ptr, CommExport* e) {
+  memset(e, 0, sizeof(*e));
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  if (p_cuMemGetAddressRange(&base, &size, (CUdeviceptr)ptr) != CUDA_SUCCESS) CGPTB_ERR("cuMemGetAddressRange failed");
+  cudaIpcMemHandle_t h;
+  CUDA_CHECK(cudaIpcGetMemHandle(&h, (void*)base));
+  static_assert(sizeof(h) == sizeof(e->handle), "ipc handle size");
+  memcpy(e->handle, &h, sizeof(h));
+  e->offset = (unsigned long long)((CUdeviceptr)ptr - base);
+}
+
+void* comm_import(int rank, const CommExport* e) {
+  static std::map<std::string, void*> opened;
+  std::string key((const char*)e->handle, sizeof(e->handle));
+  key += (char)rank;
+  auto f = opened.find(key);
+  if (f == opened.end()) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, e->handle, sizeof(h));
+    void* base = 0;
+    cudaError_t err = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+    if (err != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    f = opened.emplace(key, base).first;
+  }
+  return (char*)f->second + e->offset;
+}
+
+// peer-to-peer halo path usable?  All ranks of a box, memory operations available, not switched off (CGPTB_HALO=nccl);
+// decided once, collectively (every rank tries to map an allocation of its successor).
+bool comm_p2p_available() {
+  if (p2p_state >= 0) return p2p_state == 1;
+  p2p_state = 0;
+  const char* v = getenv("CGPTB_HALO");
+  int ok = g_comm.active && !(v && !strcmp(v, "nccl")) && load_memops() ? 1 : 0;
+  void* probe = 0;
+  std::vector<CommExport> all(g_comm.world);
+  if (ok) {
+    CUDA_CHECK(cudaMalloc(&probe, 1 << 21));
+    CommExport mine;
+    comm_export(probe, &mine);
+    comm_allgather_host(&mine, all.data(), sizeof(CommExport));
+    int nb = (g_comm.rank + 1) % g_comm.world;
+    if (!comm_import(nb, &all[nb])) ok = 0;
+  }
+  // agree: one rank that cannot map its neighbour switches everybody to NCCL
+  double* d = reduce_scratch(8);
+  double h = ok ? 0.0 : 1.0;
+  CUDA_CHECK(cudaMemcpyAsync(d, &h, sizeof(double), cudaMemcpyHostToDevice, g_stream));
+  comm_allreduce_device(d, 1, g_stream);
+  CUDA_CHECK(cudaMemcpyAsync(&h, d, sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  CUDA_CHECK(cudaStreamSynchronize(g_stream));
+  p2p_state = h == 0.0 ? 1 : 0;
+  return p2p_state == 1;  // the probe allocation stays (a neighbour has it mapped)
+}
+
+void comm_stream_write32(cudaStream_t s, void* addr, unsigned value) {
+  if (p_cuStreamWriteValue32((CUstream)s, (CUdeviceptr)addr, value, 0) != CUDA_SUCCESS) CGPTB_ERR("cuStreamWriteValue32 failed");
+}
+void comm_stream_wait_geq32(cudaStream_t s, void* addr, unsigned value) {
+  if (p_cuStreamWaitValue32((CUstream)s, (CUdeviceptr)addr, value, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) CGPTB_ERR("cuStreamWaitValue32 failed");
 }
 
 }  // namespace cgptb

@@ -41,6 +41,17 @@ void comm_exchange_begin();
 void comm_exchange_dir(int mu, const void* to_lo, const void* to_hi, void* from_lo, void* from_hi, size_t bytes, cudaStream_t s);
 void comm_exchange_end();
 void comm_allreduce_device(double* dev, int n, cudaStream_t s);
+struct CommExport {  // what a rank publishes about a device allocation its neighbours may write into
+  unsigned char handle[64];
+  unsigned long long offset;
+};
+void comm_allgather_host(const void* in, void* out, size_t bytes);
+void comm_allgather_device(const void* in, void* out, size_t bytes, cudaStream_t s);
+bool comm_p2p_available();
+void comm_export(void* ptr, CommExport* e);
+void* comm_import(int rank, const CommExport* e);  // 0 if the allocation cannot be mapped
+void comm_stream_write32(cudaStream_t s, void* addr, unsigned value);
+void comm_stream_wait_geq32(cudaStream_t s, void* addr, unsigned value);
 extern bool g_reduce_global;
 
 struct Error {

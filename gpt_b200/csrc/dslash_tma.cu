@@ -46,30 +46,36 @@ constexpr int SC = 4;                  // fifth-dimension slices per chunk (4 x 
 constexpr int NS = TX * TY * TZ;       // 64 sites per time slice
 constexpr int NCOMP = NS * SC;         // compute threads
 constexpr int NTHREADS = NCOMP + 128;  // + producer warp group (one warp works; setmaxnreg hands its registers to the consumers)
-constexpr int REGS_PRODUCER = 40, REGS_CONSUMER = 232;  // 128 x 40 + 256 x 232 = 64512 <= 65536
+constexpr int REGS_PRODUCER = 72, REGS_CONSUMER = 216;  // 128 x 72 + 256 x 216 = 64512 <= 65536
 constexpr int ROW_B = 128;
-// one component plane of a slice slot: centre rows [z][y][x], then the six faces (16 rows each)
-constexpr int OFF_C = 0, OFF_XM = 8192, OFF_XP = 10240, OFF_YM = 12288, OFF_YP = 14336, OFF_ZM = 16384, OFF_ZP = 18432;
-constexpr int PLANE_B = 20480;
-constexpr int SLOT_B = 3 * PLANE_B;            // 61440
-constexpr int CENTER_B = 3 * NS * ROW_B;       // 24576: bytes of a centre-only load
-constexpr int FACE_B = 3 * 3 * (NS / TX) * ROW_B;  // 18432: three faces x three planes (the face part of one half step)
-// links come in two halves of four, in the order a step uses them: A = {t-, x+, x-, y+}, B = {y-, z+, z-, t+};
-// a row is 4 x 72 B + 16 B padding (bank shift of 12 words per site: the 8 sites a warp reads are conflict free)
+// shared memory rings.  A sub-step (one chunk of one time slice) needs: the centre box of the tile (64 rows of 128 B per
+// 32-byte component plane), the faces of its first half (A: x-, x+, y+, 16 rows each) and of its second half (B: y-, z+, z-); a
+// time step needs the tile's links in two halves of four, in the order a step uses them: A = {t-, x+, x-, y+}, B = {y-, z+,
+// z-, t+}.  Each class has its own ring with its own full / empty mbarriers, so a buffer is refilled as soon as ITS last reader
+// is done: centre boxes three deep (requested 2 sub-steps before use), A faces two deep (1.5), B faces three deep (2.5: the z
+// faces are what misses in L2), link halves three deep (G >= 2; a half lives for G sub-steps) or four deep (G = 1).
+// Every box carries its three component planes (fifth tensor dimension), so a sub-step is 7 TMA instructions: the TMA unit
+// spends ~100 cycles per instruction whatever the box size, which bounded the memory side at 28 instructions per sub-step.
+constexpr int CENTER1_B = NS * ROW_B;           // 8192: one plane of a centre box, rows [z][y][x]
+constexpr int FACE1_B = (NS / TX) * ROW_B;      // 2048: one plane of a face
+constexpr int CENTER_B = 3 * CENTER1_B;         // 24576: a centre box [plane][z][y][x]
+constexpr int FACE_B = 3 * FACE1_B;             // 6144: a face [plane][16 rows]
+constexpr int FACES_B = 3 * FACE_B;             // 18432: a face set (three faces)
+// a link row is 4 x 72 B + 16 B padding (bank shift of 12 words per site: the 8 sites a warp reads are conflict free)
 constexpr int LINK_ROW_F = 76;
 constexpr int LINK_ROW_B = LINK_ROW_F * 4;    // 304
 constexpr int LINK_HALF_B = NS * LINK_ROW_B;  // 19456
-constexpr int HALF_B = FACE_B + LINK_HALF_B;  // 37888: bytes signalled on full_A / full_B of a full step
-constexpr int NSLOT = 2;
-// shared memory: two spinor slots (one per sub-step in flight), two link buffers (one per time step in flight, halves A | B)
-constexpr int OFF_LINKS = NSLOT * SLOT_B;                    // 122880
-constexpr int LINKBUF_B = 2 * LINK_HALF_B;                   // 38912
-constexpr int OFF_BARS = OFF_LINKS + NSLOT * LINKBUF_B;      // 200704
-// barriers per spinor slot: full_C (centre), full_A, full_B (faces of the first / second half), empty_A, empty_B;
-// per link buffer: full_A, full_B, empty_A, empty_B
-constexpr int BAR_FC = 0, BAR_FA = 1, BAR_FB = 2, BAR_EA = 3, BAR_EB = 4, NBAR = 5;
-constexpr int LBAR_FA = 0, LBAR_FB = 1, LBAR_EA = 2, LBAR_EB = 3, NLBAR = 4;
-constexpr int SMEM_B = OFF_BARS + NSLOT * (NBAR + NLBAR) * 8 + 1024;  // + alignment slack
+template <int G>
+struct Ring {
+  static constexpr int NC = 3, NFA = 2, NFB = G == 1 ? 2 : 3, NLH = G == 1 ? 4 : 3;
+  static constexpr int OFF_C = 0, OFF_FA = NC * CENTER_B, OFF_FB = OFF_FA + NFA * FACES_B;
+  static constexpr int OFF_LINKS = OFF_FB + NFB * FACES_B;
+  static constexpr int OFF_BARS = OFF_LINKS + NLH * LINK_HALF_B;  // G = 1: 225280, else 224256
+  // barriers: full then empty of each class
+  static constexpr int B_FC = 0, B_EC = NC, B_FA = 2 * NC, B_EA = B_FA + NFA, B_FB = B_EA + NFA, B_EB = B_FB + NFB, B_FL = B_EB + NFB,
+                       B_EL = B_FL + NLH, NBARS = B_EL + NLH;
+  static constexpr int SMEM_B = OFF_BARS + NBARS * 8 + 1024;  // + alignment slack
+};
 constexpr int GMAX = 3;  // chunks per CTA (register budget: G x 36 registers of open state per thread)
 
 // One unit of work: a tile x a group of G chunks of the fifth dimension x a range of time slices.  The host lays the items out
@@ -84,7 +90,6 @@ struct Geo {
   int hx, Ly, Lz, T;
   int nbx, nby, nbz, ngroup;
   int nitems;
-  int tp;  // component-plane stride of the input field in units of time slices
   int p_out;
   int ls;
   int comm_mask;  // split directions (bit 2: z, bit 3: t): hops that leave the local volume are left to the halo kernels
@@ -127,13 +132,14 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
-// spinor of one (site, s) from a slice slot: a = byte address of the low 16-byte chunk of plane 0 (swizzle applied)
-__device__ __forceinline__ void lds_spinor(uint32_t a, c32 (&p)[12]) {
-  const uint32_t b = a ^ 16u;
+// spinor of one (site, s) from a box in shared memory: a = byte address of the low 16-byte chunk in plane 0 (swizzle
+// applied), ps = distance of the component planes (centre box 8192, face 2048)
+__device__ __forceinline__ void lds_spinor(uint32_t a, uint32_t ps, c32 (&p)[12]) {
 #pragma unroll
   for (int k = 0; k < 3; k++) {
-    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(p[4 * k]), "=l"(p[4 * k + 1]) : "r"(a + k * PLANE_B));
-    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(p[4 * k + 2]), "=l"(p[4 * k + 3]) : "r"(b + k * PLANE_B));
+    const uint32_t ak = a + k * ps;
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(p[4 * k]), "=l"(p[4 * k + 1]) : "r"(ak));
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(p[4 * k + 2]), "=l"(p[4 * k + 3]) : "r"(ak ^ 16u));
   }
 }
 
@@ -212,15 +218,59 @@ __device__ __forceinline__ void hop_math(c32 (&acc)[12], const c32 (&psi)[12], c
 }
 
 template <int MU, bool FWD, bool DAG, int D>
-__device__ __forceinline__ void hop_smem(c32 (&acc)[12], uint32_t spinor_addr, uint32_t link_row) {
+__device__ __forceinline__ void hop_smem(c32 (&acc)[12], uint32_t spinor_addr, uint32_t plane_stride, uint32_t link_row) {
   c32 psi[12];
   float wr[9], wi[9];
-  lds_spinor(spinor_addr, psi);
+  lds_spinor(spinor_addr, plane_stride, psi);
   lds_link<D>(link_row, wr, wi);
   hop_math<MU, FWD, DAG>(acc, psi, wr, wi);
 }
 
-// ABL (ablation, CGPTB_ABLATE): 0 production; 1 compute only (no TMA loads, the ring is signalled empty-handed);
+// Position in a CTA's sequence of sub-steps: item (stride gridDim.x through the item table), step st of the item (0 and
+// trl + 1 are the two partial steps that only feed the t hops), chunk c of the group.  The producer keeps one cursor per
+// ring because the rings run different numbers of sub-steps ahead of the consumers.
+struct Cursor {
+  ItemDesc it;
+  int item, st, c;
+  __device__ __forceinline__ void start(const ItemDesc* items, int nitems) {
+    item = blockIdx.x;
+    st = 0;
+    c = 0;
+    if (item < nitems) it = items[item];
+  }
+  __device__ __forceinline__ bool valid(int nitems) const { return item < nitems; }
+  __device__ __forceinline__ bool full() const { return st >= 1 && st <= it.trl; }
+  __device__ __forceinline__ int tau(int T) const {
+    int t = it.t0 - 1 + st;
+    if (t < 0) t += T;
+    if (t >= T) t -= T;
+    return t;
+  }
+  template <int G>
+  __device__ __forceinline__ void next(const ItemDesc* items, int nitems) {
+    if (++c < G) return;
+    c = 0;
+    if (++st <= it.trl + 1) return;
+    st = 0;
+    item += gridDim.x;
+    if (item < nitems) it = items[item];
+  }
+  // the same over full time steps only (the steps that have links)
+  __device__ __forceinline__ void start_steps(const ItemDesc* items, int nitems) {
+    item = blockIdx.x;
+    st = 1;
+    c = 0;
+    if (item < nitems) it = items[item];
+  }
+  __device__ __forceinline__ void next_step(const ItemDesc* items, int nitems) {
+    if (++st <= it.trl) return;
+    st = 1;
+    item += gridDim.x;
+    if (item < nitems) it = items[item];
+  }
+};
+
+// ABL (ablation, CGPTB_ABLATE): 0 production; 1 compute only (no TMA loads, the rings are signalled empty-handed);
 // 2 memory only (all loads and stores, no hop arithmetic)
 // COMM: the lattice is split across GPUs in z and/or t (Geo::comm_mask); off-rank hops are skipped here and added by
 // k_exterior (halo.cu) once the faces have arrived
@@ -228,27 +278,21 @@ __device__ __forceinline__ void hop_smem(c32 (&acc)[12], uint32_t spinor_addr, u
 template <bool DAG, int ABL, bool COMM, int G>
 __global__ void __launch_bounds__(NTHREADS, 1)
     k_dhop_f32_tma(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
-                   const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmM,
+                   const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmC,
                    const __grid_constant__ CUtensorMap tmL, const Geo geo, const ItemDesc* __restrict__ items,
                    float* __restrict__ out, size_t out_stride) {
+  typedef Ring<G> R;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t s_bar = sbase + OFF_BARS, s_lbar = s_bar + NSLOT * NBAR * 8;
+  const uint32_t s_bar = sbase + R::OFF_BARS;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
+  auto bar = [&](int which, uint32_t i) -> uint32_t { return s_bar + 8u * ((uint32_t)which + i); };
 
   if (tid == 0) {
-    for (int i = 0; i < NSLOT; i++) {
-      const uint32_t b = s_bar + 8 * NBAR * i, lb = s_lbar + 8 * NLBAR * i;
-      mbar_init(b + 8 * BAR_FC, 1);
-      mbar_init(b + 8 * BAR_FA, 1);
-      mbar_init(b + 8 * BAR_FB, 1);
-      mbar_init(b + 8 * BAR_EA, NCOMP / 32);
-      mbar_init(b + 8 * BAR_EB, NCOMP / 32);
-      mbar_init(lb + 8 * LBAR_FA, 1);
-      mbar_init(lb + 8 * LBAR_FB, 1);
-      mbar_init(lb + 8 * LBAR_EA, NCOMP / 32);
-      mbar_init(lb + 8 * LBAR_EB, NCOMP / 32);
+    for (int i = 0; i < R::NBARS; i++) {
+      const bool full = i < R::B_EC || (i >= R::B_FA && i < R::B_EA) || (i >= R::B_FB && i < R::B_EB) || (i >= R::B_FL && i < R::B_EL);
+      mbar_init(s_bar + 8 * i, full ? 1 : NCOMP / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -256,105 +300,72 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 
   if (warp >= NCOMP / 32) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER));
-    if (warp != NCOMP / 32) return;
-    // ---------------- producer: one elected lane -------------------------------------------------------------
-    // Each spinor slot is refilled in two halves: A = faces x-, x+, y+ as soon as the consumers are past the fourth hop of
-    // the sub-step that used the slot, then the centre box and B = faces y-, z-, z+ when the sub-step is over; the link
-    // buffer of a time step likewise (A = {t-, x+, x-, y+} after the fourth hop of the step's last sub-step, B = {y-, z+,
-    // z-, t+} at its end).  Every spinor byte is requested 1.5 sub-steps, every link 1 + 1/(2G) steps before it is needed,
-    // although only two slots fit into shared memory.  (L2 eviction-priority hints on the z faces were measured in round 1
-    // and 2: no effect on the DRAM traffic; removed.)
+    // ---------------- producers: one warp (one elected lane) per ring ----------------------------------------
+    // warp 0: A faces, 1: centre boxes, 2: B faces, 3: link halves.  Each walks the CTA's sequence of sub-steps (time steps)
+    // on its own: wait until the consumers have released the buffer that comes next in its ring, refill it.  (L2
+    // eviction-priority hints on the z faces were measured in rounds 1 and 2: no effect on the DRAM traffic; removed.)
+    const int role = warp - NCOMP / 32;
     if (lane != 0) return;
-    uint32_t g = 0, q = 0;  // sub-steps, full time steps so far
-    for (int item = blockIdx.x; item < geo.nitems; item += gridDim.x) {
-      const ItemDesc it = items[item];
-      const int xm = (it.xh0 == 0 ? geo.hx : it.xh0) - 1, xp = it.xh0 + TX == geo.hx ? 0 : it.xh0 + TX;
-      const int ym = (it.y0 == 0 ? geo.Ly : it.y0) - 1, yp = it.y0 + TY == geo.Ly ? 0 : it.y0 + TY;
-      const int zm = (it.z0 == 0 ? geo.Lz : it.z0) - 1, zp = it.z0 + TZ == geo.Lz ? 0 : it.z0 + TZ;
-      const uint32_t face1 = 3 * (NS / TX) * ROW_B;  // one face, three planes
-      const uint32_t bytesA = ((geo.skip & 1) ? 0 : 2 * face1) + ((geo.skip & 2) ? 0 : face1);
-      const uint32_t bytesB = ((geo.skip & 4) ? 0 : 2 * face1) + ((geo.skip & 2) ? 0 : face1);
+    Cursor cur;
+    if (role == 3) {
       const bool load_links = ABL != 1 && !(geo.skip & 8);
-      for (int st = 0; st <= it.trl + 1; st++) {
-        int tau = it.t0 - 1 + st;
-        if (tau < 0) tau += geo.T;
-        if (tau >= geo.T) tau -= geo.T;
-        const bool full_step = st >= 1 && st <= it.trl;
-        const uint32_t lbar = s_lbar + 8 * NLBAR * (q & 1u), lph = (q >> 1) & 1u;
-        const uint32_t dlink = sbase + OFF_LINKS + (q & 1u) * LINKBUF_B;
-        for (int c = 0; c < G; c++, g++) {
-          const int s0f = (it.c * G + c) * SC * 8;
-          const uint32_t slot = g & 1u, ph = (g >> 1) & 1u;
-          const uint32_t bar = s_bar + 8 * NBAR * slot;
-          const uint32_t dst = sbase + slot * SLOT_B;
-          // half A
-          if (c == 0 && full_step) {
-            mbar_wait(lbar + 8 * LBAR_EA, lph ^ 1u);
-            if (load_links) {
-              mbar_expect_tx(lbar + 8 * LBAR_FA, (uint32_t)LINK_HALF_B);
-              tma_load_5d(dlink, &tmL, lbar + 8 * LBAR_FA, 0, it.xh0, it.y0, it.z0, tau);
-            } else {
-              mbar_arrive(lbar + 8 * LBAR_FA);
-            }
+      cur.start_steps(items, geo.nitems);
+      for (uint32_t n = 0; cur.valid(geo.nitems); n++) {
+        const uint32_t i = n % R::NLH, par = (n / R::NLH) & 1u;
+        mbar_wait(bar(R::B_EL, i), par ^ 1u);
+        if (load_links) {
+          const int tau = cur.tau(geo.T);
+          mbar_expect_tx(bar(R::B_FL, i), (uint32_t)LINK_HALF_B);
+          tma_load_5d(sbase + R::OFF_LINKS + i * LINK_HALF_B, &tmL, bar(R::B_FL, i), 0, cur.it.xh0, cur.it.y0, cur.it.z0,
+                      (n & 1u) ? geo.T + tau : tau);
+        } else {
+          mbar_arrive(bar(R::B_FL, i));
+        }
+        if (n & 1u) cur.next_step(items, geo.nitems);
+      }
+      return;
+    }
+    const uint32_t bytesA = ((geo.skip & 1) ? 0 : 2 * FACE_B) + ((geo.skip & 2) ? 0 : FACE_B);
+    const uint32_t bytesB = ((geo.skip & 4) ? 0 : 2 * FACE_B) + ((geo.skip & 2) ? 0 : FACE_B);
+    const uint32_t depth = role == 0 ? R::NFA : role == 1 ? R::NC : R::NFB;
+    const int b_full = role == 0 ? R::B_FA : role == 1 ? R::B_FC : R::B_FB, b_empty = role == 0 ? R::B_EA : role == 1 ? R::B_EC : R::B_EB;
+    const uint32_t bytes = role == 0 ? bytesA : role == 1 ? (uint32_t)CENTER_B : bytesB;
+    cur.start(items, geo.nitems);
+    uint32_t i = 0, par = 0;
+    for (; cur.valid(geo.nitems); cur.next<G>(items, geo.nitems)) {
+      const uint32_t fb = bar(b_full, i);
+      mbar_wait(bar(b_empty, i), par ^ 1u);
+      if (ABL == 1 || bytes == 0 || (role != 1 && !cur.full())) {
+        mbar_arrive(fb);
+      } else {
+        mbar_expect_tx(fb, bytes);
+        const ItemDesc& it = cur.it;
+        const int s0f = (it.c * G + cur.c) * SC * 8, zt = geo.Lz * cur.tau(geo.T);  // fourth coordinate = z + Lz * t
+        if (role == 0) {
+          const int xm = (it.xh0 == 0 ? geo.hx : it.xh0) - 1, xp = it.xh0 + TX == geo.hx ? 0 : it.xh0 + TX;
+          const int yp = it.y0 + TY == geo.Ly ? 0 : it.y0 + TY;
+          const uint32_t d = sbase + R::OFF_FA + i * FACES_B;
+          if (!(geo.skip & 1)) {
+            tma_load_5d(d, &tmX, fb, s0f, xm, it.y0, zt + it.z0, 0);
+            tma_load_5d(d + FACE_B, &tmX, fb, s0f, xp, it.y0, zt + it.z0, 0);
           }
-          mbar_wait(bar + 8 * BAR_EA, ph ^ 1u);
-          if (ABL == 1 || !full_step || bytesA == 0) {
-            mbar_arrive(bar + 8 * BAR_FA);
-          } else {
-            mbar_expect_tx(bar + 8 * BAR_FA, bytesA);
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-              const int tq = k * geo.tp + tau;
-              const uint32_t d = dst + k * PLANE_B;
-              if (!(geo.skip & 1)) {
-                tma_load_5d(d + OFF_XP, &tmX, bar + 8 * BAR_FA, s0f, xp, it.y0, it.z0, tq);
-                tma_load_5d(d + OFF_XM, &tmX, bar + 8 * BAR_FA, s0f, xm, it.y0, it.z0, tq);
-              }
-              if (!(geo.skip & 2)) tma_load_5d(d + OFF_YP, &tmY, bar + 8 * BAR_FA, s0f, it.xh0, yp, it.z0, tq);
-            }
-          }
-          // centre and half B
-          mbar_wait(bar + 8 * BAR_EB, ph ^ 1u);
-          if (ABL == 1) {
-            mbar_arrive(bar + 8 * BAR_FC);
-          } else {
-            mbar_expect_tx(bar + 8 * BAR_FC, (uint32_t)CENTER_B);
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-              // centre box as bottom layer, two middle layers, top layer (rows [z][y][x]: 16 rows per layer)
-              const uint32_t d = dst + k * PLANE_B + OFF_C;
-              const int tq = k * geo.tp + tau;
-              tma_load_5d(d, &tmZ, bar + 8 * BAR_FC, s0f, it.xh0, it.y0, it.z0, tq);
-              tma_load_5d(d + 16 * ROW_B, &tmM, bar + 8 * BAR_FC, s0f, it.xh0, it.y0, it.z0 + 1, tq);
-              tma_load_5d(d + 48 * ROW_B, &tmZ, bar + 8 * BAR_FC, s0f, it.xh0, it.y0, it.z0 + 3, tq);
-            }
-          }
-          if (c == 0 && full_step) {
-            mbar_wait(lbar + 8 * LBAR_EB, lph ^ 1u);
-            if (load_links) {
-              mbar_expect_tx(lbar + 8 * LBAR_FB, (uint32_t)LINK_HALF_B);
-              tma_load_5d(dlink + LINK_HALF_B, &tmL, lbar + 8 * LBAR_FB, 0, it.xh0, it.y0, it.z0, geo.T + tau);
-            } else {
-              mbar_arrive(lbar + 8 * LBAR_FB);
-            }
-          }
-          if (ABL == 1 || !full_step || bytesB == 0) {
-            mbar_arrive(bar + 8 * BAR_FB);
-          } else {
-            mbar_expect_tx(bar + 8 * BAR_FB, bytesB);
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-              const int tq = k * geo.tp + tau;
-              const uint32_t d = dst + k * PLANE_B;
-              if (!(geo.skip & 2)) tma_load_5d(d + OFF_YM, &tmY, bar + 8 * BAR_FB, s0f, it.xh0, ym, it.z0, tq);
-              if (!(geo.skip & 4)) {
-                tma_load_5d(d + OFF_ZP, &tmZ, bar + 8 * BAR_FB, s0f, it.xh0, it.y0, zp, tq);
-                tma_load_5d(d + OFF_ZM, &tmZ, bar + 8 * BAR_FB, s0f, it.xh0, it.y0, zm, tq);
-              }
-            }
+          if (!(geo.skip & 2)) tma_load_5d(d + 2 * FACE_B, &tmY, fb, s0f, it.xh0, yp, zt + it.z0, 0);
+        } else if (role == 1) {
+          tma_load_5d(sbase + R::OFF_C + i * CENTER_B, &tmC, fb, s0f, it.xh0, it.y0, zt + it.z0, 0);
+        } else {
+          const int ym = (it.y0 == 0 ? geo.Ly : it.y0) - 1;
+          const int zm = (it.z0 == 0 ? geo.Lz : it.z0) - 1, zp = it.z0 + TZ == geo.Lz ? 0 : it.z0 + TZ;
+          const uint32_t d = sbase + R::OFF_FB + i * FACES_B;
+          if (!(geo.skip & 2)) tma_load_5d(d, &tmY, fb, s0f, it.xh0, ym, zt + it.z0, 0);
+          if (!(geo.skip & 4)) {
+            tma_load_5d(d + FACE_B, &tmZ, fb, s0f, it.xh0, it.y0, zt + zp, 0);
+            tma_load_5d(d + 2 * FACE_B, &tmZ, fb, s0f, it.xh0, it.y0, zt + zm, 0);
           }
         }
-        if (full_step) q++;
+      }
+      if (++i == depth) {
+        i = 0;
+        par ^= 1u;
       }
     }
     return;
@@ -362,16 +373,25 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 
   // ---------------- consumers: thread = (site l of the tile, slice j of each of the G chunks) -------------
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_CONSUMER));
-  const int l = tid >> 2, j = tid & 3;
-  const int lx = l & 3, ly = (l >> 2) & 3, lz = l >> 4;
-  auto rowaddr = [&](int buf, int row) -> uint32_t { return (uint32_t)(buf + row * ROW_B + (((2 * j) ^ (row & 7)) << 4)); };
-  const uint32_t a_own = rowaddr(OFF_C, l);
-  const uint32_t a_left = lx > 0 ? rowaddr(OFF_C, l - 1) : rowaddr(OFF_XM, lz * TY + ly);
-  const uint32_t a_right = lx < TX - 1 ? rowaddr(OFF_C, l + 1) : rowaddr(OFF_XP, lz * TY + ly);
-  const uint32_t a_yp = ly < TY - 1 ? rowaddr(OFF_C, l + TX) : rowaddr(OFF_YP, lz * TX + lx);
-  const uint32_t a_ym = ly > 0 ? rowaddr(OFF_C, l - TX) : rowaddr(OFF_YM, lz * TX + lx);
-  const uint32_t a_zp = lz < TZ - 1 ? rowaddr(OFF_C, l + TX * TY) : rowaddr(OFF_ZP, ly * TX + lx);
-  const uint32_t a_zm = lz > 0 ? rowaddr(OFF_C, l - TX * TY) : rowaddr(OFF_ZM, ly * TX + lx);
+  // a warp owns two x rows of the tile, (y, z) and (y + 1, z ^ 1): the parity of y + z, and with it which of the two x
+  // neighbours of a checkerboard site is the site's own x/2 index, is then uniform in the warp, so that hop can take the
+  // thread's own spinor from registers instead of reading it from shared memory a second time
+  const int j = tid & 3, lx = (tid >> 2) & 3, row = (tid >> 4) & 1;
+  const int ly = 2 * (warp & 1) + row, lz = (warp >> 1) ^ row;
+  const int l = lx + TX * (ly + TY * lz);
+  // offset of this thread's 16-byte chunk in row `row` of a buffer (128-byte swizzle; buffers are 1 KB aligned)
+  auto rowoff = [&](int row) -> uint32_t { return (uint32_t)(row * ROW_B + (((2 * j) ^ (row & 7)) << 4)); };
+  // neighbours: inside the centre box (planes 8192 B apart), or a row of a face (A: [x-][x+][y+], B: [y-][z+][z-]; 16 rows per
+  // plane, planes 2048 B apart)
+  const uint32_t o_own = rowoff(l);
+  const bool f_left = lx == 0, f_right = lx == TX - 1, f_yp = ly == TY - 1, f_ym = ly == 0, f_zp = lz == TZ - 1, f_zm = lz == 0;
+  const uint32_t o_left = f_left ? rowoff(lz * TY + ly) : rowoff(l - 1);
+  const uint32_t o_right = f_right ? FACE_B + rowoff(lz * TY + ly) : rowoff(l + 1);
+  const uint32_t o_yp = f_yp ? 2 * FACE_B + rowoff(lz * TX + lx) : rowoff(l + TX);
+  const uint32_t o_ym = f_ym ? rowoff(lz * TX + lx) : rowoff(l - TX);
+  const uint32_t o_zp = f_zp ? FACE_B + rowoff(ly * TX + lx) : rowoff(l + TX * TY);
+  const uint32_t o_zm = f_zm ? 2 * FACE_B + rowoff(ly * TX + lx) : rowoff(l - TX * TY);
+  auto pstride = [](bool face) -> uint32_t { return face ? (uint32_t)FACE1_B : (uint32_t)CENTER1_B; };
   const int b0 = (ly + lz + geo.p_out) & 1;  // tile origins are even
   const int slice_sites = geo.hx * geo.Ly * geo.Lz;
 
@@ -389,7 +409,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 #pragma unroll
   for (int k = 0; k < 9; k++) utr[k] = uti[k] = 0.f;
 
-  uint32_t g = 0, q = 0;
+  uint32_t q = 0;  // full time steps so far
+  uint32_t iC = 0, pC = 0, iA = 0, pA = 0, iB = 0, pB = 0;  // ring positions and phase parities of the current sub-step
   for (int item = blockIdx.x; item < geo.nitems; item += gridDim.x) {
     const ItemDesc it = items[item];
     const int site0 = (it.xh0 + lx) + geo.hx * ((it.y0 + ly) + geo.Ly * (it.z0 + lz));
@@ -399,19 +420,18 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       if (tau < 0) tau += geo.T;
       if (tau >= geo.T) tau -= geo.T;
       const bool full_step = st >= 1 && st <= it.trl;
-      const uint32_t lbar = s_lbar + 8 * NLBAR * (q & 1u), lph = (q >> 1) & 1u;
-      const uint32_t lrowA = sbase + OFF_LINKS + (q & 1u) * LINKBUF_B + l * LINK_ROW_B, lrowB = lrowA + LINK_HALF_B;
+      const uint32_t hA = 2 * q, hB = 2 * q + 1;
+      const uint32_t iLA = hA % R::NLH, pLA = (hA / R::NLH) & 1u, iLB = hB % R::NLH, pLB = (hB / R::NLH) & 1u;
+      const uint32_t lrowA = sbase + R::OFF_LINKS + iLA * LINK_HALF_B + l * LINK_ROW_B;
+      const uint32_t lrowB = sbase + R::OFF_LINKS + iLB * LINK_HALF_B + l * LINK_ROW_B;
       const int b = (b0 + tau) & 1;
-      const uint32_t a_xp = b ? a_right : a_own, a_xm = b ? a_own : a_left;
 #pragma unroll
-      for (int c = 0; c < G; c++, g++) {
+      for (int c = 0; c < G; c++) {
         const int s = (it.c * G + c) * SC + j;
-        const uint32_t slot = g & 1u, ph = (g >> 1) & 1u;
-        const uint32_t bar = s_bar + 8 * NBAR * slot;
-        const uint32_t sp = sbase + slot * SLOT_B;
-        mbar_wait(bar + 8 * BAR_FC, ph);
+        const uint32_t cb = sbase + R::OFF_C + iC * CENTER_B, fa = sbase + R::OFF_FA + iA * FACES_B, fb = sbase + R::OFF_FB + iB * FACES_B;
+        mbar_wait(bar(R::B_FC, iC), pC);
         c32 own[12];
-        lds_spinor(sp + a_own, own);
+        lds_spinor(cb + o_own, CENTER1_B, own);
         if (st >= 2) {
           // forward-t hop closes the output of the previous slice
           if (ABL != 2 && !(COMM && (geo.comm_mask & 8) && tau_prev == geo.T - 1)) hop_math<3, true, DAG>(acc[c], own, utr, uti);
@@ -425,8 +445,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           }
         }
         // ---- first half: t-, x+, x-, y+
-        mbar_wait(bar + 8 * BAR_FA, ph);
-        if (c == 0 && full_step) mbar_wait(lbar + 8 * LBAR_FA, lph);
+        mbar_wait(bar(R::B_FA, iA), pA);
+        if (c == 0 && full_step) mbar_wait(bar(R::B_FL, iLA), pLA);
         if (ABL == 2) {
 #pragma unroll
           for (int k = 0; k < 12; k++) acc[c][k] = own[k];
@@ -440,31 +460,61 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             hop_mulrecon<3, false, DAG, true>(acc[c], hc[c], wr, wi);
           }
         }
-        hop_proj<3, false, DAG>(hc[c], own);  // own is dead from here on
+        hop_proj<3, false, DAG>(hc[c], own);
         if (ABL != 2 && full_step) {
-          hop_smem<0, true, DAG, 1>(acc[c], sp + a_xp, lrowA);
-          hop_smem<0, false, DAG, 2>(acc[c], sp + a_xm, lrowA);
-          hop_smem<1, true, DAG, 3>(acc[c], sp + a_yp, lrowA);
+          // b (uniform in the warp): the forward x neighbour has x/2 + 1 and the backward one the site's own x/2, or the
+          // forward one the own x/2 and the backward one x/2 - 1.  The hop to the own x/2 takes the spinor from registers
+          // (G = 1; with more chunks the second copy of two hops costs more in instruction fetch than the 6 LDS.128 save).
+          if (G == 1) {
+            float wr[9], wi[9];
+            if (b) {
+              lds_link<2>(lrowA, wr, wi);
+              hop_math<0, false, DAG>(acc[c], own, wr, wi);
+              hop_smem<0, true, DAG, 1>(acc[c], (f_right ? fa : cb) + o_right, pstride(f_right), lrowA);
+            } else {
+              lds_link<1>(lrowA, wr, wi);
+              hop_math<0, true, DAG>(acc[c], own, wr, wi);
+              hop_smem<0, false, DAG, 2>(acc[c], (f_left ? fa : cb) + o_left, pstride(f_left), lrowA);
+            }
+          } else {
+            const uint32_t a_right = (f_right ? fa : cb) + o_right, a_left = (f_left ? fa : cb) + o_left;
+            hop_smem<0, true, DAG, 1>(acc[c], b ? a_right : cb + o_own, b ? pstride(f_right) : (uint32_t)CENTER1_B, lrowA);
+            hop_smem<0, false, DAG, 2>(acc[c], b ? cb + o_own : a_left, b ? (uint32_t)CENTER1_B : pstride(f_left), lrowA);
+          }
+          hop_smem<1, true, DAG, 3>(acc[c], (f_yp ? fa : cb) + o_yp, pstride(f_yp), lrowA);
         }
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(bar + 8 * BAR_EA);
-          if (c == G - 1 && full_step) mbar_arrive(lbar + 8 * LBAR_EA);
+          mbar_arrive(bar(R::B_EA, iA));
+          if (c == G - 1 && full_step) mbar_arrive(bar(R::B_EL, iLA));
         }
         // ---- second half: y-, z+, z-, and U_t for the forward-t hops of the next step
-        mbar_wait(bar + 8 * BAR_FB, ph);
-        if (c == 0 && full_step) mbar_wait(lbar + 8 * LBAR_FB, lph);
+        mbar_wait(bar(R::B_FB, iB), pB);
+        if (c == 0 && full_step) mbar_wait(bar(R::B_FL, iLB), pLB);
         if (ABL != 2 && full_step) {
-          hop_smem<1, false, DAG, 0>(acc[c], sp + a_ym, lrowB);
-          // lz is uniform within a warp (8 consecutive sites), so these branches do not diverge
-          if (!(COMM && (geo.comm_mask & 4) && it.z0 + lz == geo.Lz - 1)) hop_smem<2, true, DAG, 1>(acc[c], sp + a_zp, lrowB);
-          if (!(COMM && (geo.comm_mask & 4) && it.z0 + lz == 0)) hop_smem<2, false, DAG, 2>(acc[c], sp + a_zm, lrowB);
+          hop_smem<1, false, DAG, 0>(acc[c], (f_ym ? fb : cb) + o_ym, pstride(f_ym), lrowB);
+          // (z split: the two x rows of a warp have different z, the boundary predicates are per row)
+          if (!(COMM && (geo.comm_mask & 4) && it.z0 + lz == geo.Lz - 1)) hop_smem<2, true, DAG, 1>(acc[c], (f_zp ? fb : cb) + o_zp, pstride(f_zp), lrowB);
+          if (!(COMM && (geo.comm_mask & 4) && it.z0 + lz == 0)) hop_smem<2, false, DAG, 2>(acc[c], (f_zm ? fb : cb) + o_zm, pstride(f_zm), lrowB);
           if (c == G - 1) lds_link<3>(lrowB, utr, uti);
         }
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(bar + 8 * BAR_EB);
-          if (c == G - 1 && full_step) mbar_arrive(lbar + 8 * LBAR_EB);
+          mbar_arrive(bar(R::B_EC, iC));
+          mbar_arrive(bar(R::B_EB, iB));
+          if (c == G - 1 && full_step) mbar_arrive(bar(R::B_EL, iLB));
+        }
+        if (++iC == R::NC) {
+          iC = 0;
+          pC ^= 1u;
+        }
+        if (++iA == R::NFA) {
+          iA = 0;
+          pA ^= 1u;
+        }
+        if (++iB == R::NFB) {
+          iB = 0;
+          pB ^= 1u;
         }
       }
       if (full_step) q++;
@@ -641,11 +691,11 @@ void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, s
   G.nbx = g.hx / TX;
   G.nby = g.L[1] / TY;
   G.nbz = g.L[2] / TZ;
-  // chunks per CTA: the largest divisor of the number of chunks that the register budget allows (CGPTB_TMA_G overrides)
+  // chunks per CTA.  Default 1: measured on B200 at 32^3 x 64 x 12 (profiles/ablation_r2.txt) G = 1 and G = 3 are within 3 % of
+  // each other -- G = 3 moves 7 % less DRAM and 20 % less L2->SM traffic, G = 1 has a third of the code and the own-spinor
+  // reuse --, G = 1 ahead.  CGPTB_TMA_G selects another divisor of Ls / 4 up to GMAX.
   const int nchunk = ls / SC;
   int ng = 1;
-  for (int d = 1; d <= GMAX; d++)
-    if (nchunk % d == 0) ng = d;
   const int ng_env = env_i("CGPTB_TMA_G", 0);
   if (ng_env >= 1 && ng_env <= GMAX && nchunk % ng_env == 0) ng = ng_env;
   G.ngroup = nchunk / ng;
@@ -654,26 +704,22 @@ void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, s
     t_count = G.T;
   }
   CGPTB_ASSERT(t_begin >= 0 && t_begin + t_count <= G.T);
-  const size_t slice_blocks = (size_t)g.hx * g.L[1] * g.L[2] * ls;  // 32-byte blocks per time slice
-  CGPTB_ASSERT(in_stride % slice_blocks == 0);
-  G.tp = (int)(in_stride / slice_blocks);
   G.p_out = p_out;
   G.ls = ls;
   G.skip = env_i("CGPTB_TMA_SKIP", 0);
   G.comm_mask = g.comm_mask;
-  // box shapes: one x column, one y row, one z layer (also the bottom / top layer of the centre box), two z layers (its middle)
-  CUtensorMap tmX, tmY, tmZ, tmM, tmL;
+  // the field as a 5-d tensor (s * 8 floats, x/2, y, z + Lz * t, component plane); boxes with all three planes: one x column,
+  // one y row, one z layer, the tile
+  CUtensorMap tmX, tmY, tmZ, tmC, tmL;
   {
-    const cuuint64_t dims[5] = {(cuuint64_t)ls * 8, (cuuint64_t)g.hx, (cuuint64_t)g.L[1], (cuuint64_t)g.L[2],
-                                (cuuint64_t)2 * G.tp + g.L[3]};
+    const cuuint64_t dims[5] = {(cuuint64_t)ls * 8, (cuuint64_t)g.hx, (cuuint64_t)g.L[1], (cuuint64_t)g.L[2] * g.L[3], 3};
     const cuuint64_t row = (cuuint64_t)ls * 32;
-    const cuuint64_t strides[4] = {row, row * g.hx, row * g.hx * g.L[1], row * g.hx * g.L[1] * g.L[2]};
-    const cuuint32_t bx[5] = {SC * 8, 1, TY, TZ, 1}, by[5] = {SC * 8, TX, 1, TZ, 1}, bz[5] = {SC * 8, TX, TY, 1, 1};
+    const cuuint64_t strides[4] = {row, row * g.hx, row * g.hx * g.L[1], (cuuint64_t)in_stride * 32};
+    const cuuint32_t bx[5] = {SC * 8, 1, TY, TZ, 3}, by[5] = {SC * 8, TX, 1, TZ, 3}, bz[5] = {SC * 8, TX, TY, 1, 3}, bc[5] = {SC * 8, TX, TY, TZ, 3};
     encode5(&tmX, pin, dims, strides, bx, CU_TENSOR_MAP_SWIZZLE_128B);
     encode5(&tmY, pin, dims, strides, by, CU_TENSOR_MAP_SWIZZLE_128B);
     encode5(&tmZ, pin, dims, strides, bz, CU_TENSOR_MAP_SWIZZLE_128B);
-    const cuuint32_t bm[5] = {SC * 8, TX, TY, 2, 1};
-    encode5(&tmM, pin, dims, strides, bm, CU_TENSOR_MAP_SWIZZLE_128B);
+    encode5(&tmC, pin, dims, strides, bc, CU_TENSOR_MAP_SWIZZLE_128B);
   }
   {
     const cuuint64_t dims[5] = {(cuuint64_t)LINK_ROW_F, (cuuint64_t)g.hx, (cuuint64_t)g.L[1], (cuuint64_t)g.L[2],
@@ -685,8 +731,9 @@ void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, s
   }
   const int grid_env = env_i("CGPTB_TMA_GRID", 0);
   // a persistent grid on every SM would keep the NCCL send/recv kernels of the halo exchange from being scheduled until
-  // the stencil is done, so a split lattice leaves a few SMs free for them (CGPTB_TMA_COMM_SMS)
-  int grid = grid_env > 0 ? grid_env : sm_count() - (g.comm_mask ? env_i("CGPTB_TMA_COMM_SMS", 8) : 0);
+  // the stencil is done, so a split lattice leaves a few SMs free for them (CGPTB_TMA_COMM_SMS) -- unless the halo goes
+  // through peer memory (halo.cu), which needs no communication kernel
+  int grid = grid_env > 0 ? grid_env : sm_count() - (g.comm_mask && !halo_is_p2p(op) ? env_i("CGPTB_TMA_COMM_SMS", 8) : 0);
   if (grid < 1) grid = 1;
   const ItemDesc* items = schedule_on_device(G, grid, t_begin, t_count, env_i("CGPTB_TMA_SCHED", 1), env_i("CGPTB_TMA_TRL", 16), &G.nitems);
   if (grid > G.nitems) grid = G.nitems;
@@ -694,8 +741,10 @@ void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, s
   typedef void (*kernel_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const Geo,
                            const ItemDesc*, float*, size_t);
   kernel_t kern = 0;
+  int smem_b = 0;
 #define TMA_PICK(G_)                                                                                  \
   if (ng == G_) {                                                                                     \
+    smem_b = Ring<G_>::SMEM_B;                                                                        \
     if (g.comm_mask)                                                                                  \
       kern = dag ? k_dhop_f32_tma<true, 0, true, G_> : k_dhop_f32_tma<false, 0, true, G_>;            \
     else if (abl == 1)                                                                                \
@@ -712,10 +761,10 @@ void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, s
   CGPTB_ASSERT(kern != 0);
   static std::map<kernel_t, bool> configured;
   if (!configured[kern]) {
-    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B));
+    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b));
     configured[kern] = true;
   }
-  kern<<<grid, NTHREADS, SMEM_B, g_stream>>>(tmX, tmY, tmZ, tmM, tmL, G, items, pout, out_stride);
+  kern<<<grid, NTHREADS, smem_b, g_stream>>>(tmX, tmY, tmZ, tmC, tmL, G, items, pout, out_stride);
   LAUNCH_CHECK();
 }
 

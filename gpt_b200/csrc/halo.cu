@@ -2,13 +2,27 @@
 // T, then Z (then Y); per Dslash each split direction exchanges one face of spin-projected half-spinors
 // (12 reals per 5d site) with each neighbour:
 //
+// Default on one box (all ranks can map each other's memory, CUDA IPC): everything on the compute stream,
+//
+//   pack faces, storing them INTO the neighbours' receive buffers over NVLink -> cuStreamWriteValue32 of the call number into
+//   the neighbours' flag words -> interior stencil (all local hops, all SMs) -> cuStreamWaitValue32 on the own flag words ->
+//   exterior update
+//
+// so the transfer is the pack kernel's own stores, no communication kernel takes SMs from the persistent stencil and no
+// second stream or event is involved.  Receive buffers alternate with the call number; a buffer is safe to overwrite two
+// calls later because the exchange is symmetric: the neighbour's data of call n+1 -- which this rank waits for before it
+// can pack call n+2 -- was packed after the neighbour's exterior kernel of call n in its stream.
+// Fallback (CGPTB_HALO=nccl, or memory that cannot be mapped):
+//
 //   compute stream : pack faces -> [event] -> interior stencil (all local hops) -> wait -> exterior update
 //   comm stream    :               wait -> NCCL send/recv group over NVLink -> [event]
 //
-// so the transfer is hidden behind the interior kernel.  Links on the low face (U_mu(x-mu) of the
+// Either way the transfer is hidden behind the interior kernel.  Links on the low face (U_mu(x-mu) of the
 // neighbour) are fetched once at gauge import, so the receiver does the SU(3) multiply for both faces.
 // This is what Grid's CartesianStencil::HaloExchange + overlapCommsCompute do for the reference
 // (lib/cgpt/lib/operators/mobius.h:52, wilson_clover.h:45).
+#include <utility>
+#include <vector>
 #include "dslash.cuh"
 #include "operator.cuh"
 
@@ -156,16 +170,41 @@ __global__ void k_pack_links(Geom g, FaceGeom fg, size_t nsU, const TU* __restri
   }
 }
 
+// Peer-to-peer state of an operator: an arena in this rank's memory that the neighbours write into -- flag words [mu][side]
+// followed by the receive buffers [mu][side][call parity] --, and where the same things live in the neighbours' arenas.
+// Arenas are pooled and never freed (the neighbours keep them mapped).
+struct HaloP2P {
+  char* arena = 0;
+  size_t arena_bytes = 0;
+  size_t off_recv[4][2][2];
+  char* peer[4][2];  // arena of the neighbour at -mu (0) / +mu (1), mapped into this process
+  unsigned seq = 0;  // number of exchanges so far
+  static size_t flag_off(int mu, int side) { return (size_t)(mu * 2 + side) * 128; }
+};
+struct ArenaPool {
+  std::vector<std::pair<char*, size_t>> free_list;
+};
+static ArenaPool g_arenas;
+
+bool halo_is_p2p(const cgptb_fermion_operator* op) { return op->p2p != 0; }
+
 template <typename T, int MU>
 static void pack_t(cgptb_fermion_operator* op, bool dag, int q_in, const T* in, size_t in_stride) {
   FaceGeom fg = make_face(op->g, MU);
   int ls = op->ls();
   size_t nface = (size_t)(op->g.half4 / op->g.L[MU]) * ls;
   unsigned blocks = (unsigned)((2 * nface + 127) / 128);
+  T *to_lo = (T*)op->halo_send[MU][0], *to_hi = (T*)op->halo_send[MU][1];
+  if (op->p2p) {
+    // my low face is the -mu neighbour's "from_hi" (side 1), my high face the +mu neighbour's "from_lo" (side 0)
+    HaloP2P* h = (HaloP2P*)op->p2p;
+    to_lo = (T*)(h->peer[MU][0] + h->off_recv[MU][1][h->seq & 1]);
+    to_hi = (T*)(h->peer[MU][1] + h->off_recv[MU][0][h->seq & 1]);
+  }
   if (dag)
-    k_pack<T, MU, true><<<blocks, 128, 0, g_stream>>>(op->g, fg, ls, q_in, in, in_stride, (T*)op->halo_send[MU][0], (T*)op->halo_send[MU][1], nface);
+    k_pack<T, MU, true><<<blocks, 128, 0, g_stream>>>(op->g, fg, ls, q_in, in, in_stride, to_lo, to_hi, nface);
   else
-    k_pack<T, MU, false><<<blocks, 128, 0, g_stream>>>(op->g, fg, ls, q_in, in, in_stride, (T*)op->halo_send[MU][0], (T*)op->halo_send[MU][1], nface);
+    k_pack<T, MU, false><<<blocks, 128, 0, g_stream>>>(op->g, fg, ls, q_in, in, in_stride, to_lo, to_hi, nface);
   LAUNCH_CHECK();
 }
 
@@ -176,15 +215,37 @@ static void exterior_t(cgptb_fermion_operator* op, bool dag, int p_out, T* out, 
   size_t nface = (size_t)(op->g.half4 / op->g.L[MU]) * ls;
   unsigned blocks = (unsigned)((2 * nface + 127) / 128);
   const T* links = (const T*)op->links[p_out];
+  const T *from_lo = (const T*)op->halo_recv[MU][0], *from_hi = (const T*)op->halo_recv[MU][1];
+  if (op->p2p) {
+    HaloP2P* h = (HaloP2P*)op->p2p;
+    from_lo = (const T*)(h->arena + h->off_recv[MU][0][h->seq & 1]);
+    from_hi = (const T*)(h->arena + h->off_recv[MU][1][h->seq & 1]);
+  }
   if (dag)
-    k_exterior<T, MU, true><<<blocks, 128, 0, g_stream>>>(op->g, fg, ls, p_out, out, out_stride, (const T*)op->halo_recv[MU][0], (const T*)op->halo_recv[MU][1], nface, links);
+    k_exterior<T, MU, true><<<blocks, 128, 0, g_stream>>>(op->g, fg, ls, p_out, out, out_stride, from_lo, from_hi, nface, links);
   else
-    k_exterior<T, MU, false><<<blocks, 128, 0, g_stream>>>(op->g, fg, ls, p_out, out, out_stride, (const T*)op->halo_recv[MU][0], (const T*)op->halo_recv[MU][1], nface, links);
+    k_exterior<T, MU, false><<<blocks, 128, 0, g_stream>>>(op->g, fg, ls, p_out, out, out_stride, from_lo, from_hi, nface, links);
   LAUNCH_CHECK();
 }
 
 template <typename T>
 static void halo_begin_t(cgptb_fermion_operator* op, bool dag, int p_out, const T* in, size_t in_stride) {
+  if (op->p2p) {
+    HaloP2P* h = (HaloP2P*)op->p2p;
+    h->seq++;
+    for (int mu = 1; mu < 4; mu++) {
+      if (!((op->g.comm_mask >> mu) & 1)) continue;
+      if (mu == 1) pack_t<T, 1>(op, dag, 1 - p_out, in, in_stride);
+      if (mu == 2) pack_t<T, 2>(op, dag, 1 - p_out, in, in_stride);
+      if (mu == 3) pack_t<T, 3>(op, dag, 1 - p_out, in, in_stride);
+    }
+    for (int mu = 1; mu < 4; mu++) {
+      if (!((op->g.comm_mask >> mu) & 1)) continue;
+      comm_stream_write32(g_stream, h->peer[mu][0] + HaloP2P::flag_off(mu, 1), h->seq);
+      comm_stream_write32(g_stream, h->peer[mu][1] + HaloP2P::flag_off(mu, 0), h->seq);
+    }
+    return;
+  }
   for (int mu = 1; mu < 4; mu++) {
     if (!((op->g.comm_mask >> mu) & 1)) continue;
     if (mu == 1) pack_t<T, 1>(op, dag, 1 - p_out, in, in_stride);
@@ -205,7 +266,16 @@ static void halo_begin_t(cgptb_fermion_operator* op, bool dag, int p_out, const 
 
 template <typename T>
 static void halo_end_t(cgptb_fermion_operator* op, bool dag, int p_out, T* out, size_t out_stride) {
-  CUDA_CHECK(cudaStreamWaitEvent(g_stream, g_comm.ev_comm, 0));
+  if (op->p2p) {
+    HaloP2P* h = (HaloP2P*)op->p2p;
+    for (int mu = 1; mu < 4; mu++) {
+      if (!((op->g.comm_mask >> mu) & 1)) continue;
+      comm_stream_wait_geq32(g_stream, h->arena + HaloP2P::flag_off(mu, 0), h->seq);
+      comm_stream_wait_geq32(g_stream, h->arena + HaloP2P::flag_off(mu, 1), h->seq);
+    }
+  } else {
+    CUDA_CHECK(cudaStreamWaitEvent(g_stream, g_comm.ev_comm, 0));
+  }
   for (int mu = 1; mu < 4; mu++) {
     if (!((op->g.comm_mask >> mu) & 1)) continue;
     if (mu == 1) exterior_t<T, 1>(op, dag, p_out, out, out_stride);
@@ -237,11 +307,51 @@ void halo_setup(cgptb_fermion_operator* op, const cgptb_lattice* const U[4]) {
   op->g.comm_mask = 0;
   if (!g_comm.active) return;
   size_t real = op->prec == CGPTB_SINGLE ? 4 : 8;
+  const bool p2p = comm_p2p_available();
+  if (p2p && !op->p2p) {
+    // arena: flag words, then the receive buffers; taken from the pool of released arenas if one is large enough
+    HaloP2P* h = new HaloP2P;
+    size_t off = 4096;
+    for (int mu = 1; mu < 4; mu++) {
+      if (g_comm.pgrid[mu] == 1) continue;
+      size_t bytes = (((size_t)(op->g.half4 / op->g.L[mu]) * op->ls() * 12 * real) + 255) & ~(size_t)255;
+      for (int side = 0; side < 2; side++)
+        for (int par = 0; par < 2; par++) {
+          h->off_recv[mu][side][par] = off;
+          off += bytes;
+        }
+    }
+    h->arena_bytes = off;
+    for (size_t i = 0; i < g_arenas.free_list.size(); i++)
+      if (g_arenas.free_list[i].second >= off) {
+        h->arena = g_arenas.free_list[i].first;
+        h->arena_bytes = g_arenas.free_list[i].second;
+        g_arenas.free_list.erase(g_arenas.free_list.begin() + i);
+        break;
+      }
+    if (!h->arena) CUDA_CHECK(cudaMalloc(&h->arena, h->arena_bytes));
+    // flags start at zero BEFORE any neighbour learns about this arena (the all-gather below)
+    CUDA_CHECK(cudaMemsetAsync(h->arena, 0, 4096, g_stream));
+    CUDA_CHECK(cudaStreamSynchronize(g_stream));
+    CommExport mine;
+    comm_export(h->arena, &mine);
+    std::vector<CommExport> all(g_comm.world);
+    comm_allgather_host(&mine, all.data(), sizeof(CommExport));
+    for (int mu = 1; mu < 4; mu++) {
+      if (g_comm.pgrid[mu] == 1) continue;
+      for (int side = 0; side < 2; side++) {
+        int nb = comm_neighbor_rank(mu, side ? +1 : -1);
+        h->peer[mu][side] = (char*)comm_import(nb, &all[nb]);
+        if (!h->peer[mu][side]) CGPTB_ERR("cannot map the halo arena of rank %d (set CGPTB_HALO=nccl)", nb);
+      }
+    }
+    op->p2p = h;
+  }
   for (int mu = 1; mu < 4; mu++) {
     if (g_comm.pgrid[mu] == 1) continue;
     op->g.comm_mask |= 1 << mu;
     size_t bytes = (size_t)(op->g.half4 / op->g.L[mu]) * op->ls() * 12 * real;
-    for (int side = 0; side < 2; side++) {
+    for (int side = 0; side < 2 && !p2p; side++) {
       if (!op->halo_send[mu][side]) CUDA_CHECK(cudaMalloc(&op->halo_send[mu][side], bytes));
       if (!op->halo_recv[mu][side]) CUDA_CHECK(cudaMalloc(&op->halo_recv[mu][side], bytes));
     }
@@ -267,6 +377,17 @@ void halo_setup(cgptb_fermion_operator* op, const cgptb_lattice* const U[4]) {
     CUDA_CHECK(cudaFree(snd));
     CUDA_CHECK(cudaFree(dummy));
   }
+}
+
+// the arena goes back to the pool: the neighbours have it mapped, and none of them writes into it any more (every
+// store into it belonged to an exchange this rank has waited for)
+void halo_release(cgptb_fermion_operator* op) {
+  if (!op->p2p) return;
+  HaloP2P* h = (HaloP2P*)op->p2p;
+  cudaStreamSynchronize(g_stream);
+  g_arenas.free_list.push_back(std::make_pair(h->arena, h->arena_bytes));
+  delete h;
+  op->p2p = 0;
 }
 
 }  // namespace cgptb

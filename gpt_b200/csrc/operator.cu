@@ -105,8 +105,20 @@ static void dhop_half(cgptb_fermion_operator* op, bool dag, const cgptb_lattice*
   const size_t blk_reals = 32 / sizeof(T);
   if (in->cb == CGPTB_FULL) pin += (size_t)(1 - p_out) * half * blk_reals;
   if (out->cb == CGPTB_FULL) pout += (size_t)p_out * half * blk_reals;
+  // CGPTB_HALO_TIMING=1: device time of the three phases of a decomposed Dslash (pack + signal | interior | wait + exterior),
+  // accumulated over the calls and printed every 200 calls -- a measurement aid, it synchronises the stream
+  static int timing = -1;
+  if (timing < 0) timing = getenv("CGPTB_HALO_TIMING") ? 1 : 0;
+  static cudaEvent_t tev[4];
+  static double tacc[3] = {0, 0, 0};
+  static int tcalls = 0;
+  const bool timed = timing == 1 && op->g.comm_mask;
+  if (timed && tcalls == 0 && tacc[0] == 0)
+    for (int i = 0; i < 4; i++) cudaEventCreate(&tev[i]);
+  if (timed) cudaEventRecord(tev[0], g_stream);
   // split lattice: faces go out first, the interior stencil hides the transfer, then the boundary update
   if (op->g.comm_mask) halo_begin(op, dag, p_out, pin, in->sites);
+  if (timed) cudaEventRecord(tev[1], g_stream);
   if (sizeof(T) == 4 && !use_generic_dhop()) {
     dhop_half_f32(op, dag, (const float*)pin, in->sites, (float*)pout, out->sites, p_out);
   } else {
@@ -118,7 +130,21 @@ static void dhop_half(cgptb_fermion_operator* op, bool dag, const cgptb_lattice*
       k_dhop<T, false><<<blocks, threads, 0, g_stream>>>(op->g, ls, p_out, pin, in->sites, pout, out->sites, (const T*)op->links[p_out]);
     LAUNCH_CHECK();
   }
+  if (timed) cudaEventRecord(tev[2], g_stream);
   if (op->g.comm_mask) halo_end(op, dag, p_out, pout, out->sites);
+  if (timed) {
+    cudaEventRecord(tev[3], g_stream);
+    cudaEventSynchronize(tev[3]);
+    for (int i = 0; i < 3; i++) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, tev[i], tev[i + 1]);
+      tacc[i] += ms;
+    }
+    if (++tcalls % 200 == 0) {
+      fprintf(stderr, "[halo timing rank %d] per half Dslash: pack+signal %.1f us, interior %.1f us, wait+exterior %.1f us (%d calls)\n", g_comm.rank,
+              1e3 * tacc[0] / tcalls, 1e3 * tacc[1] / tcalls, 1e3 * tacc[2] / tcalls, tcalls);
+    }
+  }
 }
 
 // results vanish on the global time slices 0 and T-1 (lib/gpt/qcd/fermion/boundary_conditions.py:23-31); in the device layout
@@ -587,12 +613,19 @@ __device__ inline void store_compact(T* dst, size_t n, size_t i, int blk, const 
 // one thread per site of parity p: field strength of the six planes from the un-phased links
 // (reference/wilson_clover.py:96-104), the two 6x6 blocks and their inverses, always in double.
 template <typename TU, typename T>
-__global__ void __launch_bounds__(64) k_build_clover(Geom g, int p, size_t nsU, const TU* U0, const TU* U1, const TU* U2,
-                                                     const TU* U3, CloverCoef cc, T* __restrict__ clov, T* __restrict__ clov_inv) {
+__global__ void __launch_bounds__(64) k_build_clover(Geom gl, Geom g, int off0, int off1, int off2, int off3, int p, size_t nsU,
+                                                     const TU* U0, const TU* U1, const TU* U2, const TU* U3, CloverCoef cc,
+                                                     T* __restrict__ clov, T* __restrict__ clov_inv) {
+  // gl: the local lattice the blocks are stored for; g, nsU, U*: the lattice the links live on -- the same, or the global
+  // lattice of a decomposed run (the field strength reaches over the corners of the local volume), off = local origin in it
   int i4 = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i4 >= g.half4) return;
+  if (i4 >= gl.half4) return;
   int c[4];
-  cb_coords(g, p, i4, c[0], c[1], c[2], c[3]);
+  cb_coords(gl, p, i4, c[0], c[1], c[2], c[3]);
+  c[0] += off0;
+  c[1] += off1;
+  c[2] += off2;
+  c[3] += off3;
   const TU* U[4] = {U0, U1, U2, U3};
   double br[2][36], bi[2][36];
   for (int b = 0; b < 2; b++)
@@ -640,9 +673,9 @@ __global__ void __launch_bounds__(64) k_build_clover(Geom g, int p, size_t nsU, 
       }
   }
   for (int b = 0; b < 2; b++) {
-    store_compact<T>(clov, g.half4, i4, b, br[b], bi[b]);
+    store_compact<T>(clov, gl.half4, i4, b, br[b], bi[b]);
     inv6(br[b], bi[b]);
-    store_compact<T>(clov_inv, g.half4, i4, b, br[b], bi[b]);
+    store_compact<T>(clov_inv, gl.half4, i4, b, br[b], bi[b]);
   }
 }
 
@@ -860,6 +893,28 @@ void cgptb_fermion_operator::setup_mobius_tables() {
   }
 }
 
+// local blocks of a colour-matrix field, one per rank as ncclAllGather delivers them, -> the field on the global lattice
+template <typename TU>
+__global__ void k_assemble_global(Geom gg, Geom gl, int pg0, int pg1, int pg2, int pg3, size_t ns_local, const TU* __restrict__ blocks,
+                                  TU* __restrict__ global) {
+  size_t site = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (site >= (size_t)2 * gg.half4) return;
+  int p = site >= (size_t)gg.half4 ? 1 : 0;
+  int c[4];
+  cb_coords(gg, p, (int)(site - (size_t)p * gg.half4), c[0], c[1], c[2], c[3]);
+  const int pc[4] = {c[0] / gl.L[0], c[1] / gl.L[1], c[2] / gl.L[2], c[3] / gl.L[3]};
+  const int rank = pc[0] + pg0 * (pc[1] + pg1 * (pc[2] + pg2 * pc[3]));
+  (void)pg3;
+  const int x = c[0] % gl.L[0], y = c[1] % gl.L[1], z = c[2] % gl.L[2], t = c[3] % gl.L[3];
+  const size_t ls = (size_t)((x + y + z + t) & 1) * gl.half4 + cb_index(gl, x, y, z, t);
+  const TU* src = blocks + (size_t)rank * ns_local * 18;
+  for (int k = 0; k < 9; k++) {
+    size_t o = elem_offset<TU>(ns_local, ls, k, 1), og = elem_offset<TU>((size_t)2 * gg.half4, site, k, 1);
+    global[og] = src[o];
+    global[og + 1] = src[o + 1];
+  }
+}
+
 template <typename TU, typename T>
 static void import_gauge_t(cgptb_fermion_operator* op, const cgptb_lattice* const U[4]) {
   LinkCoef lc;
@@ -885,12 +940,11 @@ static void import_gauge_t(cgptb_fermion_operator* op, const cgptb_lattice* cons
     LAUNCH_CHECK();
   }
   op->has_clover = op->type == CGPTB_WILSON_CLOVER && (op->p.csw_r != 0.0 || op->p.csw_t != 0.0);
-  if (op->has_clover && op->g.comm_mask) CGPTB_ERR("the clover term on a split lattice is not implemented yet (needs corner halos of U)");
   if (op->has_clover) {
     CloverCoef cc;
     cc.diag = op->p.mass + 1.0 + 3.0 * op->p.nu / op->p.xi_0;
     cc.open_bc = op->open_bc ? 1 : 0;
-    cc.T = op->dims4[3];
+    cc.T = op->gL[3];
     cc.edge = -0.5 * op->p.csw_t;
     cc.cF1 = op->p.cF - 1.0;
     // gamma matrices (lib/gpt/core/gamma.py:28-41) as (re,im) 4x4
@@ -921,15 +975,44 @@ static void import_gauge_t(cgptb_fermion_operator* op, const cgptb_lattice* cons
             cc.sim[plane][i * 4 + j] = 0.5 * si;
           }
       }
+    // The field strength at a site needs links up to one step away in two directions, i.e. across the faces AND the corners
+    // of a rank's volume.  On a decomposed lattice every rank therefore assembles the global (un-phased) links once -- an
+    // all-gather of the local blocks over NVLink, 4 x 18 reals per global site, one box has the memory -- and builds its own
+    // blocks from them; nothing of this is on the per-Dslash path.
+    Geom gU = op->g;
+    size_t nsU = U[0]->sites;
+    const TU* Ug[4] = {(const TU*)U[0]->data, (const TU*)U[1]->data, (const TU*)U[2]->data, (const TU*)U[3]->data};
+    TU* global[4] = {0, 0, 0, 0};
+    TU* blocks = 0;
+    int off[4] = {0, 0, 0, 0};
+    if (op->g.comm_mask) {
+      gU = make_geom(op->gL);
+      nsU = (size_t)2 * gU.half4;
+      const size_t local_reals = U[0]->sites * 18;
+      CUDA_CHECK(cudaMalloc(&blocks, local_reals * g_comm.world * sizeof(TU)));
+      for (int mu = 0; mu < 4; mu++) {
+        CUDA_CHECK(cudaMalloc(&global[mu], nsU * 18 * sizeof(TU)));
+        comm_allgather_device(U[mu]->data, blocks, local_reals * sizeof(TU), g_stream);
+        k_assemble_global<TU><<<(unsigned)((nsU + 127) / 128), 128, 0, g_stream>>>(gU, op->g, g_comm.pgrid[0], g_comm.pgrid[1], g_comm.pgrid[2],
+                                                                                  g_comm.pgrid[3], U[0]->sites, blocks, global[mu]);
+        LAUNCH_CHECK();
+        Ug[mu] = global[mu];
+        off[mu] = op->goff[mu];
+      }
+    }
     size_t cl_bytes = (size_t)op->g.half4 * 72 * sizeof(T);
     unsigned cblocks = (unsigned)((op->g.half4 + 63) / 64);
     for (int p = 0; p < 2; p++) {
       if (!op->clov[p]) CUDA_CHECK(cudaMalloc(&op->clov[p], cl_bytes));
       if (!op->clov_inv[p]) CUDA_CHECK(cudaMalloc(&op->clov_inv[p], cl_bytes));
-      k_build_clover<TU, T><<<cblocks, 64, 0, g_stream>>>(op->g, p, U[0]->sites, (const TU*)U[0]->data, (const TU*)U[1]->data,
-                                                          (const TU*)U[2]->data, (const TU*)U[3]->data, cc, (T*)op->clov[p],
-                                                          (T*)op->clov_inv[p]);
+      k_build_clover<TU, T><<<cblocks, 64, 0, g_stream>>>(op->g, gU, off[0], off[1], off[2], off[3], p, nsU, Ug[0], Ug[1], Ug[2], Ug[3], cc,
+                                                          (T*)op->clov[p], (T*)op->clov_inv[p]);
       LAUNCH_CHECK();
+    }
+    if (blocks) {
+      CUDA_CHECK(cudaStreamSynchronize(g_stream));
+      CUDA_CHECK(cudaFree(blocks));
+      for (int mu = 0; mu < 4; mu++) CUDA_CHECK(cudaFree(global[mu]));
     }
   }
 }
@@ -1280,6 +1363,7 @@ int cgptb_delete_fermion_operator(cgptb_fermion_operator* op) {
   CGPTB_API_BEGIN
   if (op) {
     dhop_tma_release(op);
+    halo_release(op);
     for (int p = 0; p < 2; p++) {
       if (op->links[p]) cudaFree(op->links[p]);
       if (op->clov[p]) cudaFree(op->clov[p]);

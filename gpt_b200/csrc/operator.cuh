@@ -39,6 +39,7 @@ struct cgptb_fermion_operator {
   void* halo_send[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};  // [mu][lo,hi] projected faces of one parity
   void* halo_recv[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
   void* ghost_links[4] = {0, 0, 0, 0};  // U_mu on the high face of the rank-mu neighbour (double)
+  void* p2p = 0;                        // peer-to-peer halo state (halo.cu: HaloP2P) when the ranks can map each other's memory
 
   int ls() const { return Ls > 0 ? Ls : 1; }
   void check_field(const cgptb_lattice* l) const;
@@ -70,4 +71,6 @@ void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, s
 void halo_setup(cgptb_fermion_operator* op, const cgptb_lattice* const U[4]);
 void halo_begin(cgptb_fermion_operator* op, bool dag, int p_out, const void* in, size_t in_stride);
 void halo_end(cgptb_fermion_operator* op, bool dag, int p_out, void* out, size_t out_stride);
+void halo_release(cgptb_fermion_operator* op);
+bool halo_is_p2p(const cgptb_fermion_operator* op);
 }  // namespace cgptb

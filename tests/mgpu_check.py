@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--mpi", default=None)
     ap.add_argument("--dims", default="8.8.8.16")
     ap.add_argument("--Ls", type=int, default=6, help="Ls = 8 routes the single-precision Dslash through the TMA sweep kernel")
+    ap.add_argument("--only", default="", help="comma list of parts to run: mobius, clover, cg, solve (default: all)")
     args = ap.parse_args()
 
     import torch
@@ -56,6 +57,7 @@ def main():
     Ls = args.Ls
     phases = [1.0, -1.0, np.exp(0.4j), -1.0]
     failures = []
+    parts = set(x for x in args.only.split(",") if x) or {"mobius", "clover", "cg", "solve"}
 
     def check(tag, got, ref, tol):
         err = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
@@ -65,7 +67,7 @@ def main():
         if not ok:
             failures.append(tag)
 
-    for prec, tol in [(g.double, 1e-12), (g.single, 1e-5)]:
+    for prec, tol in [(g.double, 1e-12), (g.single, 1e-5)] if "mobius" in parts else []:
         cdt = prec.complex_dtype
         grid = g.grid(dims, prec)
         Ul = [local_block(u, dims, mpi, coor, False).astype(cdt) for u in U]
@@ -116,6 +118,60 @@ def main():
         got = g(w * src4)[:]
         check(f"wilson {prec.__name__} M", got, local_block(wo.M(s4), dims, mpi, coor, False).reshape(got.shape), tol)
 
+    # Wilson-clover on the decomposed lattice (the field strength reaches over the corners of a rank's volume: the blocks are
+    # built from the all-gathered links), anisotropic, and with open boundary conditions in the global time direction
+    for prec, tol in [(g.double, 1e-12), (g.single, 1e-5)] if "clover" in parts else []:
+        cdt = prec.complex_dtype
+        grid = g.grid(dims, prec)
+        Ug = g.qcd.gauge.from_numpy(grid, [local_block(u, dims, mpi, coor, False).astype(cdt).reshape(-1, 3, 3) for u in U])
+        Uo = [u.astype(cdt) for u in U]
+        s4 = rng.cnormal(dims, (4, 3)).astype(cdt)
+        src4 = g.vspincolor(grid)
+        src4[:] = local_block(s4, dims, mpi, coor, False).reshape(-1, 4, 3)
+        for name, cp in [("clover", dict(kappa=0.13565, csw_r=2.0171 / 2.0, csw_t=2.0171 / 2.0, xi_0=1.0, nu=1.0, isAnisotropic=False, boundary_phases=phases)),
+                         ("clover aniso", dict(mass=-0.05, csw_r=1.3, csw_t=0.9, xi_0=1.7, nu=1.2, isAnisotropic=True, boundary_phases=[1.0, 1.0, 1.0, -1.0])),
+                         ("clover open", dict(kappa=0.135, csw_r=1.978, csw_t=1.978, cF=1.3, xi_0=1.0, nu=1.0, isAnisotropic=False, boundary_phases=[1.0, 1.0, 1.0, 0.0]))]:
+            w = g.qcd.fermion.wilson_clover(Ug, dict(cp))
+            wo = qcd.wilson_clover(Uo, **cp)
+            for tag, mat, ref in [("M", w, wo.M(s4)), ("Mdag", w.adj(), wo.Mdag(s4)), ("Mdiag", w.Mdiag, wo.Mooee(s4)),
+                                  ("MooeeInv", None, wo.MooeeInv(s4))]:
+                if mat is None:
+                    # the inverse blocks, through the even-odd entry on both parities
+                    full = g.vspincolor(grid)
+                    full[:] = 0
+                    for cb in [g.even, g.odd]:
+                        half = g.vspincolor(w.F_grid_eo)
+                        g.pick_checkerboard(cb, half, src4)
+                        g.set_checkerboard(full, g(w.Mooee.inv() * half))
+                    got = full[:]
+                else:
+                    got = g(mat * src4)[:]
+                check(f"{name} {prec.__name__} {tag}", got, local_block(ref, dims, mpi, coor, False).reshape(got.shape), tol)
+
+    # BASELINE.json configs[3] in small: Wilson-clover, defect-correcting mixed-precision (double outer / single inner) even-odd CG
+    # on the decomposed lattice (tests/manual/mpi.py:104-110), against the oracle's double-precision solution
+    if "solve" in parts:
+        cp = dict(kappa=0.137, csw_r=1.1, csw_t=1.1, xi_0=1.0, nu=1.0, isAnisotropic=False, boundary_phases=[1.0, 1.0, 1.0, -1.0])
+        grid = g.grid(dims, g.double)
+        Ug = g.qcd.gauge.from_numpy(grid, [local_block(u, dims, mpi, coor, False).reshape(-1, 3, 3) for u in U])
+        w = g.qcd.fermion.wilson_clover(Ug, dict(cp))
+        wo = qcd.wilson_clover(U, **cp)
+        s4 = rng.cnormal(dims, (4, 3))
+        src4 = g.vspincolor(grid)
+        src4[:] = local_block(s4, dims, mpi, coor, False).reshape(-1, 4, 3)
+        inv = g.algorithms.inverter
+        pc = g.qcd.fermion.preconditioner
+        slv = inv.defect_correcting(inv.mixed_precision(inv.preconditioned(pc.eo2_ne(), inv.cg(eps=1e-4, maxiter=1000)), g.single, g.double),
+                                    eps=1e-10, maxiter=20)
+        dst = g(slv(w) * src4)
+        res = (g.norm2(g(w * dst - src4)) / g.norm2(src4)) ** 0.5
+        ref, hist = qcd.solve_eo2_ne(wo, s4, 1e-11, 2000)
+        check("clover mixed-precision solve", dst[:], local_block(ref, dims, mpi, coor, False).reshape(-1, 4, 3), 1e-8)
+        if rank == 0:
+            print(f"clover mixed-precision solve: true residual {res:.3e} (oracle CG {len(hist)} iterations)", flush=True)
+        if not res < 1e-9:
+            failures.append(f"solve residual {res}")
+
     # eo2_ne CG in double: identical iteration count, same solution
     grid = g.grid(dims, g.double)
     Ug = g.qcd.gauge.from_numpy(grid, [local_block(u, dims, mpi, coor, False).reshape(-1, 3, 3) for u in U])
@@ -126,7 +182,7 @@ def main():
     src = g.vspincolor(op.F_grid)
     src[:] = local_block(s5, dims, mpi, coor, True).reshape(-1, 4, 3)
     inv = g.algorithms.inverter
-    for fused in [True, False]:
+    for fused in [True, False] if "cg" in parts else []:
         if not fused:
             os.environ["GPT_B200_NO_FUSED"] = "1"
         cg = inv.cg(eps=1e-8, maxiter=400)

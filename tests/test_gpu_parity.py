@@ -456,12 +456,13 @@ def test_tma_sweep_kernel_geometries(g, dims, Ls, monkeypatch):
         l1 = from_spinor(g(op * src), s5)
         monkeypatch.delenv("CGPTB_NO_TMA")
         assert rel(l1, ref) < TOL["single"]
-        # default: G = 3 / 2 / 1 chunks of four s-slices per CTA (the largest that divides Ls / 4); CGPTB_TMA_G forces another
-        # split, CGPTB_TMA_GRID few CTAs (many items per CTA), CGPTB_TMA_SCHED=0 fixed time ranges of CGPTB_TMA_TRL slices
-        for env in ({}, {"CGPTB_TMA_GRID": "1"}, {"CGPTB_TMA_GRID": "5", "CGPTB_TMA_G": "1"}, {"CGPTB_TMA_GRID": "7", "CGPTB_TMA_G": "2"},
-                    {"CGPTB_TMA_SCHED": "0", "CGPTB_TMA_GRID": "1", "CGPTB_TMA_TRL": "2"},
-                    {"CGPTB_TMA_SCHED": "0", "CGPTB_TMA_GRID": "5", "CGPTB_TMA_TRL": "4", "CGPTB_TMA_G": "1"},
-                    {"CGPTB_TMA_SCHED": "0", "CGPTB_TMA_GRID": "3", "CGPTB_TMA_TRL": "1"}):
+        # default: one chunk of four s-slices per CTA; CGPTB_TMA_G = 2 / 3 chunks per CTA (ignored unless it divides Ls / 4),
+        # CGPTB_TMA_GRID few CTAs (many items per CTA), CGPTB_TMA_SCHED=0 fixed time ranges of CGPTB_TMA_TRL slices
+        for env in ({}, {"CGPTB_TMA_GRID": "1", "CGPTB_TMA_G": "3"}, {"CGPTB_TMA_GRID": "5", "CGPTB_TMA_G": "3"}, {"CGPTB_TMA_GRID": "7", "CGPTB_TMA_G": "2"},
+                    {"CGPTB_TMA_G": "3"}, {"CGPTB_TMA_G": "2"},
+                    {"CGPTB_TMA_SCHED": "0", "CGPTB_TMA_GRID": "1", "CGPTB_TMA_TRL": "2", "CGPTB_TMA_G": "3"},
+                    {"CGPTB_TMA_SCHED": "0", "CGPTB_TMA_GRID": "5", "CGPTB_TMA_TRL": "4"},
+                    {"CGPTB_TMA_SCHED": "0", "CGPTB_TMA_GRID": "3", "CGPTB_TMA_TRL": "1", "CGPTB_TMA_G": "2"}):
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
             got = from_spinor(g(op * src), s5)

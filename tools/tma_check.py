@@ -74,9 +74,9 @@ def check():
         qm, src = setup(dims, Ls, 11)
         for dag in (False, True):
             ref = apply(qm, src, dag, {"CGPTB_NO_TMA": "1"})
-            for env in ({}, {"CGPTB_TMA_GRID": "1"}, {"CGPTB_TMA_GRID": "5", "CGPTB_TMA_G": "1"}, {"CGPTB_TMA_GRID": "7", "CGPTB_TMA_G": "2"},
-                        {"CGPTB_TMA_SCHED": "0", "CGPTB_TMA_GRID": "1", "CGPTB_TMA_TRL": "2"}, {"CGPTB_TMA_SCHED": "0", "CGPTB_TMA_GRID": "5", "CGPTB_TMA_TRL": "4"},
-                        {"CGPTB_TMA_SCHED": "0", "CGPTB_TMA_GRID": "3", "CGPTB_TMA_TRL": "1", "CGPTB_TMA_G": "1"}, {"CGPTB_TMA_SCHED": "0", "CGPTB_TMA_TRL": "64"}):
+            for env in ({}, {"CGPTB_TMA_GRID": "1", "CGPTB_TMA_G": "3"}, {"CGPTB_TMA_GRID": "5", "CGPTB_TMA_G": "3"}, {"CGPTB_TMA_GRID": "7", "CGPTB_TMA_G": "2"},
+                        {"CGPTB_TMA_G": "3"}, {"CGPTB_TMA_SCHED": "0", "CGPTB_TMA_GRID": "1", "CGPTB_TMA_TRL": "2"}, {"CGPTB_TMA_SCHED": "0", "CGPTB_TMA_GRID": "5", "CGPTB_TMA_TRL": "4", "CGPTB_TMA_G": "3"},
+                        {"CGPTB_TMA_SCHED": "0", "CGPTB_TMA_GRID": "3", "CGPTB_TMA_TRL": "1", "CGPTB_TMA_G": "2"}, {"CGPTB_TMA_SCHED": "0", "CGPTB_TMA_TRL": "64"}):
                 got = apply(qm, src, dag, dict(env))
                 err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
                 mx = np.abs(got - ref).max()
@@ -123,9 +123,10 @@ def timing():
             variants.append((name, dict(x.split("=") for x in kv.split(",") if x)))
     else:
         if os.environ.get("ABLATE"):
-            variants += [("tma compute-only", {"CGPTB_ABLATE": "1"}), ("tma memory-only", {"CGPTB_ABLATE": "2"})]
-        variants += [("tma G=1 (one chunk per CTA, round-1 work split)", {"CGPTB_TMA_G": "1"}), ("tma G=3 (all Ls per CTA)", {}),
-                     ("tma G=3 sched0 trl16", {"CGPTB_TMA_SCHED": "0"}), ("tma G=3 grid144", {"CGPTB_TMA_GRID": "144"})]
+            variants += [("tma compute-only", {"CGPTB_ABLATE": "1"}), ("tma memory-only", {"CGPTB_ABLATE": "2"}),
+                         ("tma G=3 compute-only", {"CGPTB_ABLATE": "1", "CGPTB_TMA_G": "3"}), ("tma G=3 memory-only", {"CGPTB_ABLATE": "2", "CGPTB_TMA_G": "3"})]
+        variants += [("tma G=1 (one chunk per CTA)", {}), ("tma G=3 (all Ls per CTA)", {"CGPTB_TMA_G": "3"}),
+                     ("tma G=1 sched0 trl16", {"CGPTB_TMA_SCHED": "0"}), ("tma G=1 grid144", {"CGPTB_TMA_GRID": "144"})]
     steps = int(os.environ.get("STEPS", "200"))
     for rnd in range(int(os.environ.get("ROUNDS", "2"))):
         for name, env in variants:
