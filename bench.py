@@ -145,54 +145,70 @@ def gell_mann_half():
 
 
 # ---- parity of the timed operator on the bench lattice ------------------------------------------------------------------
-def parity_check(torch, dist, cgpt, U, src, dst, dims, world, rank, n_sites4=9000):
+def parity_check(torch, dist, cgpt, U, src, dst, dims, mpi, rank, n_sites4=9000):
     """
     Compare dst = Dhop src (already computed on the device) with oracle/dslash_ref.c on sampled sites of this rank's
-    block.  The block is padded with the last / first time slice of the T-neighbours (its own, periodically, for one
-    rank), so boundary sites check the halo exchange; a quarter of the sample lies on the two boundary slices.
-    Returns (rel_err, n_5d_sites); the caller takes the max over ranks.
+    block.  The block is padded by one slice in t and in z with the faces of the neighbours in the processor grid mpi =
+    1.1.Z.T (its own, periodically, where a direction is not split), so boundary sites check the halo exchange; a quarter
+    of the sample lies on the boundary slices of each split direction.  Returns (rel_err, n_5d_sites); the caller takes the
+    max over ranks.
     """
     from oracle import cref
 
+    world = int(np.prod(mpi))
     cref.set_num_threads(max(1, cref.host_cores() // max(1, min(world, 8))))
     X, Y, Z, T = dims
-    v3 = X * Y * Z
-    slice_c = v3 * LS * 12  # complex numbers per time slice of the 5d field
-    psi = np.empty((T + 2) * slice_c, dtype=np.complex64)
-    cgpt.lattice_export_ptr(src.obj, psi[slice_c:].ctypes.data, T * slice_c * 8)
-    V = np.empty((4, (T + 2) * v3 * 9), dtype=np.complex64)
-    for mu in range(4):
-        cgpt.lattice_export_ptr(U[mu].obj, V[mu, v3 * 9:].ctypes.data, T * v3 * 9 * 8)
+    assert mpi[0] == 1 and mpi[1] == 1, "parity check: T and Z splits"
+    pz, pt = mpi[2], mpi[3]
+    cz, ct = rank % pz, rank // pz
 
-    def neighbours(first, last):
-        """(last slice of the rank below, first slice of the rank above) of a per-rank pair of boundary slices"""
+    def padded(lat, ncomp):
+        """local field in GPT order -> [T + 2, Z + 2, Y * X * ncomp] with the neighbours' faces"""
+        row = Y * X * ncomp
+        flat = np.empty(T * Z * row, dtype=np.complex64)
+        cgpt.lattice_export_ptr(lat.obj, flat.ctypes.data, flat.nbytes)
+        P = np.zeros((T + 2, Z + 2, row), dtype=np.complex64)
+        P[1:-1, 1:-1] = flat.reshape(T, Z, row)
+        del flat
+        faces = {"t_lo": P[1, 1:-1], "t_hi": P[T, 1:-1], "z_lo": P[1:-1, 1], "z_hi": P[1:-1, Z]}
         if world == 1:
-            return last, first
-        mine = torch.from_numpy(np.stack([first, last])).cuda()
-        every = torch.empty((world,) + tuple(mine.shape), dtype=mine.dtype, device="cuda")
-        dist.all_gather_into_tensor(every, mine)
-        lo, hi = (rank - 1) % world, (rank + 1) % world  # mpi = 1.1.1.N: the rank is the T coordinate
-        return every[lo, 1].cpu().numpy(), every[hi, 0].cpu().numpy()
+            got = {k: v.copy() for k, v in faces.items()}
+            nb = lambda key, dz, dt: got[key]  # noqa: E731
+        else:
+            every = {}
+            for k, v in faces.items():
+                mine = torch.from_numpy(np.ascontiguousarray(v)).cuda()
+                ev = torch.empty((world,) + tuple(mine.shape), dtype=mine.dtype, device="cuda")
+                dist.all_gather_into_tensor(ev, mine)
+                every[k] = ev
+            nb = lambda key, dz, dt: every[key][((cz + dz) % pz) + pz * ((ct + dt) % pt)].cpu().numpy()  # noqa: E731
+        P[0, 1:-1] = nb("t_hi", 0, -1)
+        P[T + 1, 1:-1] = nb("t_lo", 0, +1)
+        P[1:-1, 0] = nb("z_hi", -1, 0)
+        P[1:-1, Z + 1] = nb("z_lo", +1, 0)
+        return P
 
-    lo, hi = neighbours(psi[slice_c:2 * slice_c].copy(), psi[T * slice_c:(T + 1) * slice_c].copy())
-    psi[:slice_c], psi[(T + 1) * slice_c:] = lo, hi
-    n = v3 * 9
-    lo, hi = neighbours(V[:, n:2 * n].copy(), V[:, T * n:(T + 1) * n].copy())
-    V[:, :n], V[:, (T + 1) * n:] = lo, hi
+    psi = padded(src, LS * 12)
+    V = np.stack([padded(U[mu], 9) for mu in range(4)])
 
     rs = np.random.default_rng(1234 + rank)
     nb = n_sites4 // 8
     t_of = np.concatenate([np.zeros(nb, np.int64), np.full(nb, T - 1, np.int64), rs.integers(0, T, n_sites4 - 2 * nb)])
-    idx_local = rs.integers(0, v3, n_sites4) + v3 * t_of
-    idx_local = np.unique(idx_local)
-    ref = cref.dhop_sites([X, Y, Z, T + 2], LS, V.reshape(4, -1, 3, 3), psi.reshape(-1, 4, 3), idx_local + v3)
+    z_of = rs.integers(0, Z, n_sites4)
+    z_of[2 * nb:3 * nb] = 0
+    z_of[3 * nb:4 * nb] = Z - 1
+    xy = rs.integers(0, X * Y, n_sites4)
+    key = np.unique((t_of * Z + z_of) * (X * Y) + xy)
+    t_of, z_of, xy = key // (Z * X * Y), (key // (X * Y)) % Z, key % (X * Y)
+    idx_pad = ((t_of + 1) * (Z + 2) + (z_of + 1)) * (X * Y) + xy
+    ref = cref.dhop_sites([X, Y, Z + 2, T + 2], LS, V.reshape(4, -1, 3, 3), psi.reshape(-1, 4, 3), idx_pad)
     del psi, V
-    out = np.empty(T * slice_c, dtype=np.complex64)
+    out = np.empty(T * Z * Y * X * LS * 12, dtype=np.complex64)
     cgpt.lattice_export_ptr(dst.obj, out.ctypes.data, out.nbytes)
-    got = out.reshape(T * v3, LS * 12)[idx_local].reshape(-1)
+    got = out.reshape(T * Z * Y * X, LS * 12)[key].reshape(-1)
     ref = ref.reshape(-1)
     err = float(np.linalg.norm(got.astype(np.complex128) - ref) / np.linalg.norm(ref.astype(np.complex128)))
-    return err, int(idx_local.size) * LS
+    return err, int(key.size) * LS
 
 
 def allmax(torch, dist, x):
@@ -228,6 +244,9 @@ def run_native(args):
     from gpt_b200 import parallel
 
     mpi = [1, 1, 1, world]  # BASELINE.json configs[2]: "1 GPU then T-split across 2/4/8 B200" (weak scaling in T)
+    if args.mpi:
+        mpi = [int(x) for x in args.mpi.split(".")]  # e.g. 1.1.2.4: T x Z split (north_star: "T (and then Z)")
+        assert len(mpi) == 4 and int(np.prod(mpi)) == world, (mpi, world)
     if world > 1:
         parallel.setup(dist, mpi)
     dims = list(DIMS)  # local extents; weak scaling: the global lattice grows with the processor grid
@@ -237,7 +256,7 @@ def run_native(args):
     # exp(i 0.5 sum_a u_a T_a), complex normal source; every rank draws its block of the global lattice
     rng = g.random("benchmark", "vectorized_ranlux24_24_64")
     U = g.qcd.gauge.random(grid, rng, scale=0.5)
-    qm = g.qcd.fermion.mobius(U, dict(MOBIUS))
+    qm = g.qcd.fermion.mobius(U, dict(MOBIUS, link_compression=12) if args.compress else dict(MOBIUS))
     src = g.vspincolor(qm.F_grid)
     dst = g.vspincolor(qm.F_grid)
     rng.cnormal(src)
@@ -271,7 +290,7 @@ def run_native(args):
     if not args.no_parity:
         step()
         sync()
-        err, n5 = parity_check(torch, dist, cgpt, U, src, dst, dims, world, rank)
+        err, n5 = parity_check(torch, dist, cgpt, U, src, dst, dims, mpi, rank)
         err = allmax(torch, dist, err)
         parity = {"rel_err": err, "tolerance": 1e-5, "sites_checked_per_rank": n5, "ranks": world,
                   "against": "oracle/dslash_ref.c on sampled sites of every rank's block (boundary slices included)",
@@ -308,7 +327,8 @@ def run_native(args):
     gflops = FLOPS_PER_SITE * v5 * world / (ms_per_step * 1e-3) / 1e9
 
     # roofline of the dominant kernel: one launch per parity, two per step
-    bytes_per_launch = (v5 // 2) * 48 * 4 + (v4 // 2) * 8 * 18 * 4
+    # (two-row link compression: 12 reals of the link + its U(1) factor (2 reals) instead of 18)
+    bytes_per_launch = (v5 // 2) * 48 * 4 + (v4 // 2) * 8 * (14 if args.compress else 18) * 4
     launches_per_step = 2
     peak, peak_src = peaks()
     achieved = bytes_per_launch / (ms_per_step * 1e-3 / launches_per_step) / 1e9
@@ -551,6 +571,120 @@ def cpu_baseline(sample_dims, seconds, steps=None, warmup=1):
             "ms_per_step": dt * 1e3, "cpu": cpu_model, "nproc": os.cpu_count()}
 
 
+def run_config(args):
+    """The other configurations of BASELINE.json (parity-test cases and multi-GPU solves, not the driver's bench line):
+      --config wilson_clover_16   configs[0]: Wilson-clover Dhop 16^4 double, parameters of benchmarks/wilson_clover_dslash.py:29-40;
+                                  the lattice (0.1 GB) lives in L2, so L2 is flushed before every timed application
+      --config clover_solve       configs[3]: Wilson-clover 48^3 x 96, defect-correcting mixed-precision even-odd CG (double
+                                  outer / single inner, tests/manual/mpi.py:100-110) on a T x Z processor grid (--mpi 1.1.2.4)
+      --config mobius_prop        configs[4]: Moebius 64^3 x 128 Ls = 12, 12 spin-colour columns of a point-source propagator
+                                  (README.md:150-160 stack: eo2_ne CG), T-split
+    --grid x.y.z.t sets the GLOBAL lattice (smaller ones for a quick check)."""
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    numa_bind(local_rank)
+    import gpt_b200 as g
+    from gpt_b200 import cgpt, parallel
+
+    cgpt.init(local_rank)
+    dist = None
+    mpi = [int(x) for x in args.mpi.split(".")] if args.mpi else [1, 1, 1, world]
+    assert int(np.prod(mpi)) == world, (mpi, world)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        parallel.setup(dist, mpi)
+
+    def sync():
+        cgpt.accelerator_barrier()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    defaults = {"wilson_clover_16": [16, 16, 16, 16], "clover_solve": [48, 48, 48, 96], "mobius_prop": [64, 64, 64, 128]}
+    gdims = [int(x) for x in args.grid.split(".")] if args.grid else defaults[args.config]
+    rng = g.random("benchmark", "vectorized_ranlux24_24_64")
+    inv = g.algorithms.inverter
+    pc = g.qcd.fermion.preconditioner
+    clover = dict(mass=0.08, csw_r=1.0, csw_t=1.0, xi_0=1.0, nu=1, isAnisotropic=False, boundary_phases=[1, 1, 1, -1])
+    out = {"config": {"workload": args.config, "global_dims": gdims, "parallelism": "mpi " + ".".join(str(m) for m in mpi)}, "n_gpus": world,
+           "data": "synthetic (g.random(\"benchmark\") links of scale 0.5)"}
+    if args.config == "wilson_clover_16":
+        grid = g.grid(gdims, g.double)
+        qm = g.qcd.fermion.wilson_clover(g.qcd.gauge.random(grid, rng, scale=0.5), dict(clover))
+        src, dst = g.vspincolor(grid), g.vspincolor(grid)
+        rng.cnormal(src)
+        v4 = int(np.prod(gdims))
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        stream = torch.cuda.ExternalStream(cgpt.get_stream()) if hasattr(cgpt, "get_stream") else torch.cuda.current_stream()
+        for _ in range(5):
+            qm.Dhop.mat(dst, src)
+        sync()
+        ms = 0.0
+        with torch.cuda.stream(stream):
+            for _ in range(args.steps):
+                flush.fill_(1)  # 256 MB written: nothing of the lattice is left in the 126 MB L2
+                cgpt.timer_start()
+                qm.Dhop.mat(dst, src)
+                ms += cgpt.timer_stop()
+        ms /= args.steps
+        flops = 8 * 3 * (7 + 16 * 3) * v4  # benchmarks/wilson_clover_dslash.py:53
+        bytes_alg = (24 + 24 + 8 * 18) * 8 * v4  # spinor in + out, 8 double-stored links per site
+        peak, peak_src = peaks()
+        out.update({"metric": "wilson_clover_dslash_gflops", "value": flops / (ms * 1e-3) / 1e9, "unit": "GFlop/s", "steps": args.steps,
+                    "ms_per_step": ms, "dtype": "f64", "higher_is_better": True,
+                    "roofline": {"bound": "hbm", "achieved": bytes_alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                 "frac": bytes_alg / (ms * 1e-3) / 1e9 / peak, "kernel": "k_dhop<double> (one thread per site, two launches)",
+                                 "algorithmic_bytes_per_step": bytes_alg, "peak_source": peak_src,
+                                 "note": "L2 flushed before every application (the whole problem is 0.1 GB); 65536 sites = 0.9 waves of 128-thread CTAs per parity: launch / latency bound"}})
+    elif args.config == "clover_solve":
+        grid = g.grid(gdims, g.double)
+        U = g.qcd.gauge.random(grid, rng, scale=0.5)
+        qm = g.qcd.fermion.wilson_clover(U, dict(clover))
+        src = g.vspincolor(grid)
+        rng.cnormal(src)
+        cg_inner = inv.cg({"eps": 1e-4, "maxiter": 40000})
+        slv = inv.defect_correcting(inv.mixed_precision(inv.preconditioned(pc.eo2_ne(), cg_inner), g.single, g.double), eps=args.solve_eps, maxiter=100)
+        prop = slv(qm)
+        dst = g(prop * src)  # warm-up solve (operators in both precisions are built here)
+        sync()
+        t0 = time.time()
+        dst = g(prop * src)
+        sync()
+        t1 = time.time()
+        res = (g.norm2(g(qm * dst - src)) / g.norm2(src)) ** 0.5
+        out.update({"metric": "wilson_clover_mixed_precision_solve_seconds", "value": t1 - t0, "unit": "s", "higher_is_better": False, "dtype": "f64 outer / f32 inner",
+                    "solver": "defect_correcting(mixed_precision(preconditioned(eo2_ne, cg(eps=1e-4)), single, double), eps=%g)" % args.solve_eps,
+                    "true_residual": res, "inner_iterations_last_cycle": len(cg_inner.history), "converged": bool(res < 10 * args.solve_eps)})
+    else:
+        grid = g.grid(gdims, g.single)
+        U = g.qcd.gauge.random(grid, rng, scale=0.5)
+        qm = g.qcd.fermion.mobius(U, dict(MOBIUS, boundary_phases=[1.0, 1.0, 1.0, -1.0]))
+        cg = inv.cg({"eps": args.solve_eps_single, "maxiter": 20000})
+        prop = qm.propagator(inv.preconditioned(pc.eo2_ne(), cg))
+        src = g.mspincolor(grid)
+        g.create.point(src, [0, 0, 0, 0])
+        sync()
+        t0 = time.time()
+        dst = g(prop * src)
+        sync()
+        t1 = time.time()
+        corr = g.slice(g.trace(dst * g.adj(dst)), 3)
+        out.update({"metric": "mobius_12_column_propagator_seconds", "value": t1 - t0, "unit": "s", "higher_is_better": False, "dtype": "f32", "Ls": LS,
+                    "solver": "propagator(preconditioned(eo2_ne, cg(eps=%g))), 12 columns" % args.solve_eps_single, "iterations_last_column": len(cg.history),
+                    "correlator_t0_t1": [float(corr[0].real), float(corr[1].real)]})
+    if world > 1:
+        cgpt.comm_finalize()
+        dist.barrier()
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+
+
 def run_reference(args):
     """reference arm: the CPU restatement of the reference's Dhop on all host cores (Grid cannot be built here), on the
     same lattice as the native arm; under torchrun rank 0 alone runs it"""
@@ -577,6 +711,11 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--preheat", type=float, default=2.0, help="seconds the loop runs untimed before the K timed steps")
+    ap.add_argument("--mpi", default=None, help="processor grid x.y.z.t (default 1.1.1.N: T-split)")
+    ap.add_argument("--config", default="dslash", choices=["dslash", "wilson_clover_16", "clover_solve", "mobius_prop"],
+                    help="dslash: the bench line (BASELINE.json configs[2]); the others: see run_config")
+    ap.add_argument("--grid", default=None, help="global lattice x.y.z.t of a --config workload")
+    ap.add_argument("--compress", action="store_true", help="two-row SU(3) link compression (link_compression=12)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-cg", action="store_true")
@@ -591,5 +730,7 @@ if __name__ == "__main__":
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.config != "dslash":
+        run_config(a)
     else:
         run_native(a)

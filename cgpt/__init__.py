@@ -420,3 +420,29 @@ def apply_fermion_operator(op, opcode, src, dst):
     if len(src) != 1 or len(dst) != 1:
         raise RuntimeError("Assert failed: src.size() == 1 && dst.size() == 1")
     return _capi.apply_fermion_operator(op, opcode, src[0], dst[0])
+
+
+# ---- generic matrix-vector stencils ----------------------------------------------------------------------------------------
+def stencil_matrix_vector_create(lattice_matrix, lattice_vector, grid, shifts, code, code_parallel_block_size, local, matrix_parity,
+                                 vector_parity):
+    """cgpt.stencil_matrix_vector_create(lattice_matrix, lattice_vector, grid, shifts, code, code_parallel_block_size, local,
+    matrix_parity, vector_parity) -> handle  "lllOOllll"  (lib/cgpt/lib/stencil.cc:41-58).  code: list of dicts with the keys
+    target, accumulate, source, source_point, weight, factor = [(field index, point, adjoint)]
+    (lib/cgpt/lib/lattice/implementation.h stencil_matrix_vector, lib/gpt/core/local_stencil/matrix_vector.py:22-34)"""
+    g = _grid(grid)
+    if len(g.fdimensions) != 4:
+        raise RuntimeError("cgpt_b200: matrix-vector stencils live on 4d grids")
+    return _capi.stencil_matrix_vector_create(g.ldimensions, g.precision, [tuple(int(x) for x in p) for p in shifts], code,
+                                              code_parallel_block_size, local, matrix_parity, vector_parity)
+
+
+def stencil_matrix_vector_execute(stencil, matrix_fields, vector_fields, fast_osites):
+    """"lOOl"  (lib/cgpt/lib/stencil.cc:101-121): the two lists hold gpt lattices (their first v_obj is used, cgpt_basis_fill)"""
+    _capi.stencil_matrix_vector_execute(stencil, [_handle(x) for x in matrix_fields], [_handle(x) for x in vector_fields], fast_osites)
+    return 0
+
+
+def stencil_matrix_vector_delete(stencil):
+    """"l"  (lib/cgpt/lib/stencil.cc)"""
+    _capi.stencil_matrix_vector_delete(stencil)
+    return 0

@@ -23,6 +23,7 @@ from gpt_b200.gamma import gamma  # noqa: F401
 from gpt_b200.io import load, save, format  # noqa: F401,A004
 from gpt_b200 import default  # noqa: F401
 from gpt_b200.timer import timer  # noqa: F401
+from gpt_b200 import local_stencil, stencil  # noqa: F401
 import sys as _sys
 
 

@@ -36,6 +36,7 @@ class fermion_params(ctypes.Structure):
         ("mu", c_double),
         ("n_omega", c_int),
         ("omega", c_double * 128),
+        ("link_compression", c_int),
     ]
 
 
@@ -94,6 +95,9 @@ SIGNATURES = {
     "cgptb_linear_combination": (c_int, [_pp, c_int, _pp, c_int, _pd]),
     "cgptb_lattice_scale": (c_int, [c_void_p, c_double, c_double]),
     "cgptb_lattice_slice_inner_product": (c_int, [c_void_p, c_void_p, _pd]),
+    "cgptb_stencil_matrix_vector_create": (c_int, [_pp, _pi, c_int, c_int, _pi, c_int, _pi, _pd, _pi, c_int, c_int, c_int, c_int]),
+    "cgptb_stencil_matrix_vector_execute": (c_int, [c_void_p, _pp, c_int, _pp, c_int, c_int]),
+    "cgptb_stencil_matrix_vector_delete": (c_int, [c_void_p]),
     "cgptb_create_fermion_operator": (c_int, [_pp, c_int, c_int, ctypes.POINTER(fermion_params), _pp]),
     "cgptb_update_fermion_operator": (c_int, [c_void_p, _pp]),
     "cgptb_set_mass_fermion_operator": (c_int, [c_void_p, ctypes.POINTER(fermion_params)]),
@@ -355,6 +359,38 @@ def lattice_slice_inner_product(b, a, nt):
     return out
 
 
+# ---- generic matrix-vector stencil ---------------------------------------------------------------------------
+def stencil_matrix_vector_create(dims4, prec, points, code, block_size, local, matrix_parity, vector_parity):
+    """code: list of dicts target / source / source_point / accumulate / weight / factor = [(index, point, adj)]"""
+    pts = np.ascontiguousarray(np.array(points, dtype=np.int32).reshape(len(points), 4))
+    ci, w, fac = [], [], []
+    for c in code:
+        ci.append([c["target"], c["accumulate"], c["source"], c["source_point"], len(c["factor"])])
+        z = complex(c["weight"])
+        w.append([z.real, z.imag])
+        fac.extend([int(f[0]), int(f[1]), int(f[2])] for f in c["factor"])
+    ci = np.ascontiguousarray(np.array(ci, dtype=np.int32))
+    w = np.ascontiguousarray(np.array(w, dtype=np.float64))
+    fac = np.ascontiguousarray(np.array(fac if fac else [[0, 0, 0]], dtype=np.int32))
+    d = (c_int * 4)(*[int(x) for x in dims4])
+    h = c_void_p()
+    _check(_lib_ready().cgptb_stencil_matrix_vector_create(
+        ctypes.byref(h), d, _precisions[prec] if isinstance(prec, str) else prec, len(points), pts.ctypes.data_as(_pi), len(code),
+        ci.ctypes.data_as(_pi), w.ctypes.data_as(_pd), fac.ctypes.data_as(_pi), int(block_size), int(local), int(matrix_parity),
+        int(vector_parity)))
+    return h.value
+
+
+def stencil_matrix_vector_execute(h, matrix_fields, vector_fields, fast_osites=0):
+    _check(_lib_ready().cgptb_stencil_matrix_vector_execute(c_void_p(h), _handles(matrix_fields), len(matrix_fields),
+                                                            _handles(vector_fields), len(vector_fields), int(fast_osites)))
+
+
+def stencil_matrix_vector_delete(h):
+    if _lib is not None:
+        _lib.cgptb_stencil_matrix_vector_delete(c_void_p(h))
+
+
 # ---- fermion operators -----------------------------------------------------------------------------------
 def _params(p):
     fp = fermion_params()
@@ -369,6 +405,7 @@ def _params(p):
     for i, w in enumerate(omega):
         fp.omega[2 * i], fp.omega[2 * i + 1] = complex(w).real, complex(w).imag
     fp.Ls = int(p.get("Ls", 0) or 0)
+    fp.link_compression = int(p.get("link_compression", 0) or 0)
     bp = p.get("boundary_phases", [1.0, 1.0, 1.0, 1.0])
     for i in range(4):
         z = complex(bp[i])

@@ -134,6 +134,27 @@ __device__ __forceinline__ void load_link<double>(const double* __restrict__ lin
   }
 }
 
+// two-row compression: [i4][8 dirs][row 0, row 1 (6 complex), f (1 complex)]; row 2 = f conj(row 0 x row 1).  f is the U(1)
+// factor of the stored link w U (w = -c_mu/2 x boundary phase): f = w / conj(w)^2, fitted from the link itself when the table
+// is built (k_compress_links), 0 for the vanishing links of open boundary conditions
+template <typename T>
+__device__ __forceinline__ void load_link_c(const T* __restrict__ links_c, size_t i4, int dir, T (&W)[18]) {
+  const T* b = links_c + (i4 * 8 + dir) * 14;
+#pragma unroll
+  for (int k = 0; k < 12; k++) W[k] = __ldg(b + k);
+  const T fr = __ldg(b + 12), fi = __ldg(b + 13);
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const int a = (c + 1) % 3, bb = (c + 2) % 3;
+    // d = row0[a] row1[bb] - row0[bb] row1[a]
+    T dr = W[2 * a] * W[6 + 2 * bb] - W[2 * a + 1] * W[6 + 2 * bb + 1] - (W[2 * bb] * W[6 + 2 * a] - W[2 * bb + 1] * W[6 + 2 * a + 1]);
+    T di = W[2 * a] * W[6 + 2 * bb + 1] + W[2 * a + 1] * W[6 + 2 * bb] - (W[2 * bb] * W[6 + 2 * a + 1] + W[2 * bb + 1] * W[6 + 2 * a]);
+    // f conj(d)
+    W[12 + 2 * c] = fr * dr + fi * di;
+    W[12 + 2 * c + 1] = fi * dr - fr * di;
+  }
+}
+
 // neighbour checkerboard index of output site (x,y,z,t) in direction MU, forward (FWD) or backward
 template <int MU, bool FWD>
 __device__ __forceinline__ int neighbor(const Geom& g, int x, int y, int z, int t) {
@@ -154,7 +175,7 @@ __device__ __forceinline__ bool off_rank(const Geom& g, int x, int y, int z, int
 }
 
 // one direction of the stencil: acc += recon( W(^dag) proj psi(neighbour) )
-template <int MU, bool FWD, bool DAG, typename T>
+template <int MU, bool FWD, bool DAG, bool CMP = false, typename T>
 __device__ __forceinline__ void hop(T (&acc)[24], const Geom& g, int x, int y, int z, int t, int i4, int s, int ls,
                                     const T* __restrict__ in, size_t in_stride, const T* __restrict__ links) {
   // forward hop uses (1 - g_mu), backward (1 + g_mu); daggered operator swaps them
@@ -164,7 +185,10 @@ __device__ __forceinline__ void hop(T (&acc)[24], const Geom& g, int x, int y, i
   T psi[24], h[12], chi[12], W[18];
   load_spinor(in, in_stride, (size_t)n4 * ls + s, psi);
   project<MU, SGN>(psi, h);
-  load_link<T>(links, (size_t)i4, FWD ? MU : MU + 4, W);
+  if (CMP)
+    load_link_c<T>(links, (size_t)i4, FWD ? MU : MU + 4, W);
+  else
+    load_link<T>(links, (size_t)i4, FWD ? MU : MU + 4, W);
   su3_mul<!FWD>(W, h, chi);
   reconstruct_add<MU, SGN>(acc, chi);
 }

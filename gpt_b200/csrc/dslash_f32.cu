@@ -492,7 +492,7 @@ int dhop_tile_blocks(const cgptb_fermion_operator* op) {
 bool dhop_fusable(const cgptb_fermion_operator* op) {
   static int no_tiles = env_int("CGPTB_NO_TILES", 0);
   static int no_fuse = env_int("CGPTB_NO_EPILOGUE", 0);
-  if (no_tiles || no_fuse || op->prec != CGPTB_SINGLE || op->type != CGPTB_MOBIUS || op->zmobius || op->g.comm_mask) return false;
+  if (no_tiles || no_fuse || op->prec != CGPTB_SINGLE || op->type != CGPTB_MOBIUS || op->zmobius || op->g.comm_mask || op->compress) return false;
   if (!(op->Ls == 8 || op->Ls == 12 || op->Ls == 16 || op->Ls == 24)) return false;
   return dhop_tile_blocks(op) > 0;
 }

@@ -65,6 +65,10 @@ constexpr int FACES_B = 3 * FACE_B;             // 18432: a face set (three face
 constexpr int LINK_ROW_F = 76;
 constexpr int LINK_ROW_B = LINK_ROW_F * 4;    // 304
 constexpr int LINK_HALF_B = NS * LINK_ROW_B;  // 19456
+// two-row compression: a row is 4 x (rows 0 and 1 of the link: 48 B) + 4 x 8 B of U(1) factors = 224 B (bank shift 24 words)
+constexpr int LINKC_ROW_F = 56;
+constexpr int LINKC_ROW_B = LINKC_ROW_F * 4;    // 224
+constexpr int LINKC_HALF_B = NS * LINKC_ROW_B;  // 14336 (the buffers keep the size of the uncompressed halves)
 template <int G>
 struct Ring {
   static constexpr int NC = 3, NFA = 2, NFB = G == 1 ? 2 : 3, NLH = G == 1 ? 4 : 3;
@@ -167,6 +171,41 @@ __device__ __forceinline__ void lds_link(uint32_t row, float (&wr)[9], float (&w
   }
 }
 
+// the same from a compressed row: rows 0 and 1 (three LDS.128) and the U(1) factor f (LDS.64); row 2 = f conj(row 0 x row 1)
+// in packed arithmetic, 18 FFMA2 / FMUL2 per link
+template <int P>
+__device__ __forceinline__ void lds_link_c(uint32_t row, float (&wr)[9], float (&wi)[9]) {
+  const uint32_t a = row + P * 48;
+  c32 u[6], f;
+#pragma unroll
+  for (int k = 0; k < 3; k++) asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(u[2 * k]), "=l"(u[2 * k + 1]) : "r"(a + 16 * k));
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(f) : "r"(row + 192 + P * 8));
+#pragma unroll
+  for (int k = 0; k < 6; k++) upk(u[k], wr[k], wi[k]);
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const int i = (c + 1) % 3, j = (c + 2) % 3;
+    // d = u0[i] u1[j] - u0[j] u1[i]
+    c32 d = mul2(u[3 + j], bcast(wr[i]));
+    d = fma2(times_iph<1>(u[3 + j]), bcast(wi[i]), d);
+    d = fma2(u[3 + i], bcast(-wr[j]), d);
+    d = fma2(times_iph<1>(u[3 + i]), bcast(-wi[j]), d);
+    // f conj(d) = f d.re + (-i f) d.im
+    float dr, di;
+    upk(d, dr, di);
+    c32 r = mul2(f, bcast(dr));
+    r = fma2(times_iph<3>(f), bcast(di), r);
+    upk(r, wr[6 + c], wi[6 + c]);
+  }
+}
+template <int P, bool CMP>
+__device__ __forceinline__ void lds_link_any(uint32_t row, float (&wr)[9], float (&wi)[9]) {
+  if (CMP)
+    lds_link_c<P>(row, wr, wi);
+  else
+    lds_link<P>(row, wr, wi);
+}
+
 // acc += recon( W(^dag) proj psi ), same arithmetic as hop_core of dslash_f32.cu, in two pieces: the spin projection (the
 // backward-t hop carries the projected half spinor from one time slice to the next) and SU(3) x half spinor + reconstruction
 template <int MU, bool FWD, bool DAG>
@@ -217,12 +256,12 @@ __device__ __forceinline__ void hop_math(c32 (&acc)[12], const c32 (&psi)[12], c
   hop_mulrecon<MU, FWD, DAG>(acc, h, wr, wi);
 }
 
-template <int MU, bool FWD, bool DAG, int D>
+template <int MU, bool FWD, bool DAG, int D, bool CMP>
 __device__ __forceinline__ void hop_smem(c32 (&acc)[12], uint32_t spinor_addr, uint32_t plane_stride, uint32_t link_row) {
   c32 psi[12];
   float wr[9], wi[9];
   lds_spinor(spinor_addr, plane_stride, psi);
-  lds_link<D>(link_row, wr, wi);
+  lds_link_any<D, CMP>(link_row, wr, wi);
   hop_math<MU, FWD, DAG>(acc, psi, wr, wi);
 }
 
@@ -275,7 +314,8 @@ struct Cursor {
 // COMM: the lattice is split across GPUs in z and/or t (Geo::comm_mask); off-rank hops are skipped here and added by
 // k_exterior (halo.cu) once the faces have arrived
 // G: chunks of the fifth dimension per CTA (sub-steps per time step)
-template <bool DAG, int ABL, bool COMM, int G>
+// CMP: two-row link compression (the link table holds rows of LINKC_ROW_B bytes)
+template <bool DAG, int ABL, bool COMM, int G, bool CMP>
 __global__ void __launch_bounds__(NTHREADS, 1)
     k_dhop_f32_tma(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                    const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmC,
@@ -315,7 +355,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         mbar_wait(bar(R::B_EL, i), par ^ 1u);
         if (load_links) {
           const int tau = cur.tau(geo.T);
-          mbar_expect_tx(bar(R::B_FL, i), (uint32_t)LINK_HALF_B);
+          mbar_expect_tx(bar(R::B_FL, i), (uint32_t)(CMP ? LINKC_HALF_B : LINK_HALF_B));
           tma_load_5d(sbase + R::OFF_LINKS + i * LINK_HALF_B, &tmL, bar(R::B_FL, i), 0, cur.it.xh0, cur.it.y0, cur.it.z0,
                       (n & 1u) ? geo.T + tau : tau);
         } else {
@@ -422,8 +462,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       const bool full_step = st >= 1 && st <= it.trl;
       const uint32_t hA = 2 * q, hB = 2 * q + 1;
       const uint32_t iLA = hA % R::NLH, pLA = (hA / R::NLH) & 1u, iLB = hB % R::NLH, pLB = (hB / R::NLH) & 1u;
-      const uint32_t lrowA = sbase + R::OFF_LINKS + iLA * LINK_HALF_B + l * LINK_ROW_B;
-      const uint32_t lrowB = sbase + R::OFF_LINKS + iLB * LINK_HALF_B + l * LINK_ROW_B;
+      const uint32_t lrowA = sbase + R::OFF_LINKS + iLA * LINK_HALF_B + l * (CMP ? LINKC_ROW_B : LINK_ROW_B);
+      const uint32_t lrowB = sbase + R::OFF_LINKS + iLB * LINK_HALF_B + l * (CMP ? LINKC_ROW_B : LINK_ROW_B);
       const int b = (b0 + tau) & 1;
 #pragma unroll
       for (int c = 0; c < G; c++) {
@@ -456,7 +496,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             for (int k = 0; k < 12; k++) acc[c][k] = 0ull;
           } else {
             float wr[9], wi[9];
-            lds_link<0>(lrowA, wr, wi);
+            lds_link_any<0, CMP>(lrowA, wr, wi);
             hop_mulrecon<3, false, DAG, true>(acc[c], hc[c], wr, wi);
           }
         }
@@ -468,20 +508,20 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           if (G == 1) {
             float wr[9], wi[9];
             if (b) {
-              lds_link<2>(lrowA, wr, wi);
+              lds_link_any<2, CMP>(lrowA, wr, wi);
               hop_math<0, false, DAG>(acc[c], own, wr, wi);
-              hop_smem<0, true, DAG, 1>(acc[c], (f_right ? fa : cb) + o_right, pstride(f_right), lrowA);
+              hop_smem<0, true, DAG, 1, CMP>(acc[c], (f_right ? fa : cb) + o_right, pstride(f_right), lrowA);
             } else {
-              lds_link<1>(lrowA, wr, wi);
+              lds_link_any<1, CMP>(lrowA, wr, wi);
               hop_math<0, true, DAG>(acc[c], own, wr, wi);
-              hop_smem<0, false, DAG, 2>(acc[c], (f_left ? fa : cb) + o_left, pstride(f_left), lrowA);
+              hop_smem<0, false, DAG, 2, CMP>(acc[c], (f_left ? fa : cb) + o_left, pstride(f_left), lrowA);
             }
           } else {
             const uint32_t a_right = (f_right ? fa : cb) + o_right, a_left = (f_left ? fa : cb) + o_left;
-            hop_smem<0, true, DAG, 1>(acc[c], b ? a_right : cb + o_own, b ? pstride(f_right) : (uint32_t)CENTER1_B, lrowA);
-            hop_smem<0, false, DAG, 2>(acc[c], b ? cb + o_own : a_left, b ? (uint32_t)CENTER1_B : pstride(f_left), lrowA);
+            hop_smem<0, true, DAG, 1, CMP>(acc[c], b ? a_right : cb + o_own, b ? pstride(f_right) : (uint32_t)CENTER1_B, lrowA);
+            hop_smem<0, false, DAG, 2, CMP>(acc[c], b ? cb + o_own : a_left, b ? (uint32_t)CENTER1_B : pstride(f_left), lrowA);
           }
-          hop_smem<1, true, DAG, 3>(acc[c], (f_yp ? fa : cb) + o_yp, pstride(f_yp), lrowA);
+          hop_smem<1, true, DAG, 3, CMP>(acc[c], (f_yp ? fa : cb) + o_yp, pstride(f_yp), lrowA);
         }
         __syncwarp();
         if (lane == 0) {
@@ -492,11 +532,11 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         mbar_wait(bar(R::B_FB, iB), pB);
         if (c == 0 && full_step) mbar_wait(bar(R::B_FL, iLB), pLB);
         if (ABL != 2 && full_step) {
-          hop_smem<1, false, DAG, 0>(acc[c], (f_ym ? fb : cb) + o_ym, pstride(f_ym), lrowB);
+          hop_smem<1, false, DAG, 0, CMP>(acc[c], (f_ym ? fb : cb) + o_ym, pstride(f_ym), lrowB);
           // (z split: the two x rows of a warp have different z, the boundary predicates are per row)
-          if (!(COMM && (geo.comm_mask & 4) && it.z0 + lz == geo.Lz - 1)) hop_smem<2, true, DAG, 1>(acc[c], (f_zp ? fb : cb) + o_zp, pstride(f_zp), lrowB);
-          if (!(COMM && (geo.comm_mask & 4) && it.z0 + lz == 0)) hop_smem<2, false, DAG, 2>(acc[c], (f_zm ? fb : cb) + o_zm, pstride(f_zm), lrowB);
-          if (c == G - 1) lds_link<3>(lrowB, utr, uti);
+          if (!(COMM && (geo.comm_mask & 4) && it.z0 + lz == geo.Lz - 1)) hop_smem<2, true, DAG, 1, CMP>(acc[c], (f_zp ? fb : cb) + o_zp, pstride(f_zp), lrowB);
+          if (!(COMM && (geo.comm_mask & 4) && it.z0 + lz == 0)) hop_smem<2, false, DAG, 2, CMP>(acc[c], (f_zm ? fb : cb) + o_zm, pstride(f_zm), lrowB);
+          if (c == G - 1) lds_link_any<3, CMP>(lrowB, utr, uti);
         }
         __syncwarp();
         if (lane == 0) {
@@ -539,6 +579,19 @@ __global__ void k_pad_links(size_t n4, const float2* __restrict__ links, float2*
     v = links[(site * 8 + d) * 9 + e];
   }
   padded[i] = v;
+}
+
+// compressed links [site][8][14 reals] -> [half][site][4 x 12 reals, 4 x f]: same order of the directions as k_pad_links
+__global__ void k_pad_links_c(size_t n4, const float* __restrict__ links_c, float* __restrict__ padded) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4 * 2 * LINKC_ROW_F) return;
+  const int k = (int)(i % LINKC_ROW_F);
+  const size_t r = i / LINKC_ROW_F;
+  const size_t site = r % n4;
+  const int half = (int)(r / n4);
+  const int pos = k < 48 ? k / 12 : (k - 48) / 2, e = k < 48 ? k - 12 * pos : 12 + (k - 48) % 2;
+  const int d = half == 0 ? (pos == 0 ? 7 : pos == 1 ? 0 : pos == 2 ? 4 : 1) : (pos == 0 ? 5 : pos == 1 ? 2 : pos == 2 ? 6 : 3);
+  padded[i] = links_c[(site * 8 + d) * 14 + e];
 }
 
 static PFN_cuTensorMapEncodeTiled_v12000 encoder() {
@@ -673,12 +726,18 @@ void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, s
   using namespace tma;
   const Geom& g = op->g;
   const int ls = op->ls();
+  const bool cmp = op->compress;
   if (!op->links_pad_valid) {
     size_t n4 = (size_t)g.half4;
     for (int p = 0; p < 2; p++) {
       if (!op->links_pad[p]) CUDA_CHECK(cudaMalloc(&op->links_pad[p], n4 * 2 * LINK_ROW_B));
-      size_t n = n4 * 2 * 38;
-      k_pad_links<<<(unsigned)((n + 255) / 256), 256, 0, g_stream>>>(n4, (const float2*)op->links[p], (float2*)op->links_pad[p]);
+      if (cmp) {
+        size_t n = n4 * 2 * LINKC_ROW_F;
+        k_pad_links_c<<<(unsigned)((n + 255) / 256), 256, 0, g_stream>>>(n4, (const float*)op->links_c[p], (float*)op->links_pad[p]);
+      } else {
+        size_t n = n4 * 2 * 38;
+        k_pad_links<<<(unsigned)((n + 255) / 256), 256, 0, g_stream>>>(n4, (const float2*)op->links[p], (float2*)op->links_pad[p]);
+      }
       LAUNCH_CHECK();
     }
     op->links_pad_valid = true;
@@ -722,11 +781,11 @@ void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, s
     encode5(&tmC, pin, dims, strides, bc, CU_TENSOR_MAP_SWIZZLE_128B);
   }
   {
-    const cuuint64_t dims[5] = {(cuuint64_t)LINK_ROW_F, (cuuint64_t)g.hx, (cuuint64_t)g.L[1], (cuuint64_t)g.L[2],
-                                (cuuint64_t)2 * g.L[3]};  // last index = half * T + t
-    const cuuint64_t row = LINK_ROW_B;
+    const cuuint64_t rowf = cmp ? LINKC_ROW_F : LINK_ROW_F;
+    const cuuint64_t dims[5] = {rowf, (cuuint64_t)g.hx, (cuuint64_t)g.L[1], (cuuint64_t)g.L[2], (cuuint64_t)2 * g.L[3]};  // last index = half * T + t
+    const cuuint64_t row = rowf * 4;
     const cuuint64_t strides[4] = {row, row * g.hx, row * g.hx * g.L[1], row * g.hx * g.L[1] * g.L[2]};
-    const cuuint32_t bl[5] = {LINK_ROW_F, TX, TY, TZ, 1};
+    const cuuint32_t bl[5] = {(cuuint32_t)rowf, TX, TY, TZ, 1};
     encode5(&tmL, op->links_pad[p_out], dims, strides, bl, CU_TENSOR_MAP_SWIZZLE_NONE);
   }
   const int grid_env = env_i("CGPTB_TMA_GRID", 0);
@@ -742,17 +801,22 @@ void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, s
                            const ItemDesc*, float*, size_t);
   kernel_t kern = 0;
   int smem_b = 0;
-#define TMA_PICK(G_)                                                                                  \
-  if (ng == G_) {                                                                                     \
-    smem_b = Ring<G_>::SMEM_B;                                                                        \
-    if (g.comm_mask)                                                                                  \
-      kern = dag ? k_dhop_f32_tma<true, 0, true, G_> : k_dhop_f32_tma<false, 0, true, G_>;            \
-    else if (abl == 1)                                                                                \
-      kern = k_dhop_f32_tma<false, 1, false, G_>;                                                     \
-    else if (abl == 2)                                                                                \
-      kern = k_dhop_f32_tma<false, 2, false, G_>;                                                     \
-    else                                                                                              \
-      kern = dag ? k_dhop_f32_tma<true, 0, false, G_> : k_dhop_f32_tma<false, 0, false, G_>;          \
+#define TMA_PICK(G_)                                                                                          \
+  if (ng == G_) {                                                                                             \
+    smem_b = Ring<G_>::SMEM_B;                                                                                \
+    if (cmp) {                                                                                                \
+      if (g.comm_mask)                                                                                        \
+        kern = dag ? k_dhop_f32_tma<true, 0, true, G_, true> : k_dhop_f32_tma<false, 0, true, G_, true>;      \
+      else                                                                                                    \
+        kern = dag ? k_dhop_f32_tma<true, 0, false, G_, true> : k_dhop_f32_tma<false, 0, false, G_, true>;    \
+    } else if (g.comm_mask)                                                                                   \
+      kern = dag ? k_dhop_f32_tma<true, 0, true, G_, false> : k_dhop_f32_tma<false, 0, true, G_, false>;      \
+    else if (abl == 1)                                                                                        \
+      kern = k_dhop_f32_tma<false, 1, false, G_, false>;                                                      \
+    else if (abl == 2)                                                                                        \
+      kern = k_dhop_f32_tma<false, 2, false, G_, false>;                                                      \
+    else                                                                                                      \
+      kern = dag ? k_dhop_f32_tma<true, 0, false, G_, false> : k_dhop_f32_tma<false, 0, false, G_, false>;    \
   }
   TMA_PICK(1)
   TMA_PICK(2)

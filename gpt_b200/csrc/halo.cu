@@ -21,6 +21,7 @@
 // neighbour) are fetched once at gauge import, so the receiver does the SU(3) multiply for both faces.
 // This is what Grid's CartesianStencil::HaloExchange + overlapCommsCompute do for the reference
 // (lib/cgpt/lib/operators/mobius.h:52, wilson_clover.h:45).
+#include <string.h>
 #include <utility>
 #include <vector>
 #include "dslash.cuh"
@@ -188,6 +189,17 @@ static ArenaPool g_arenas;
 
 bool halo_is_p2p(const cgptb_fermion_operator* op) { return op->p2p != 0; }
 
+// CGPTB_HALO_PACK=direct: the pack kernel stores the faces straight into the neighbours' memory (one stream, no copies; the
+// kernel then runs at NVLink speed, 46 us for 2 x 9.4 MB to one peer); default: pack locally, copy engines move the faces
+static bool p2p_direct_stores() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CGPTB_HALO_PACK");
+    v = e && !strcmp(e, "direct") ? 1 : 0;
+  }
+  return v == 1;
+}
+
 template <typename T, int MU>
 static void pack_t(cgptb_fermion_operator* op, bool dag, int q_in, const T* in, size_t in_stride) {
   FaceGeom fg = make_face(op->g, MU);
@@ -195,7 +207,7 @@ static void pack_t(cgptb_fermion_operator* op, bool dag, int q_in, const T* in, 
   size_t nface = (size_t)(op->g.half4 / op->g.L[MU]) * ls;
   unsigned blocks = (unsigned)((2 * nface + 127) / 128);
   T *to_lo = (T*)op->halo_send[MU][0], *to_hi = (T*)op->halo_send[MU][1];
-  if (op->p2p) {
+  if (op->p2p && p2p_direct_stores()) {
     // my low face is the -mu neighbour's "from_hi" (side 1), my high face the +mu neighbour's "from_lo" (side 0)
     HaloP2P* h = (HaloP2P*)op->p2p;
     to_lo = (T*)(h->peer[MU][0] + h->off_recv[MU][1][h->seq & 1]);
@@ -233,17 +245,34 @@ static void halo_begin_t(cgptb_fermion_operator* op, bool dag, int p_out, const 
   if (op->p2p) {
     HaloP2P* h = (HaloP2P*)op->p2p;
     h->seq++;
+    const bool direct = p2p_direct_stores();
+    // copy-engine variant: the faces are packed into local buffers (HBM speed) and a copy engine pushes them over NVLink
+    // while the interior stencil runs; the send buffers are free again when the previous call's copies are done
+    if (!direct) CUDA_CHECK(cudaStreamWaitEvent(g_stream, g_comm.ev_comm, 0));
     for (int mu = 1; mu < 4; mu++) {
       if (!((op->g.comm_mask >> mu) & 1)) continue;
       if (mu == 1) pack_t<T, 1>(op, dag, 1 - p_out, in, in_stride);
       if (mu == 2) pack_t<T, 2>(op, dag, 1 - p_out, in, in_stride);
       if (mu == 3) pack_t<T, 3>(op, dag, 1 - p_out, in, in_stride);
     }
+    cudaStream_t cs = g_stream;
+    if (!direct) {
+      cs = g_comm.stream;
+      CUDA_CHECK(cudaEventRecord(g_comm.ev_pack, g_stream));
+      CUDA_CHECK(cudaStreamWaitEvent(cs, g_comm.ev_pack, 0));
+      for (int mu = 1; mu < 4; mu++) {
+        if (!((op->g.comm_mask >> mu) & 1)) continue;
+        size_t bytes = (size_t)(op->g.half4 / op->g.L[mu]) * op->ls() * 12 * sizeof(T);
+        CUDA_CHECK(cudaMemcpyAsync(h->peer[mu][0] + h->off_recv[mu][1][h->seq & 1], op->halo_send[mu][0], bytes, cudaMemcpyDefault, cs));
+        CUDA_CHECK(cudaMemcpyAsync(h->peer[mu][1] + h->off_recv[mu][0][h->seq & 1], op->halo_send[mu][1], bytes, cudaMemcpyDefault, cs));
+      }
+    }
     for (int mu = 1; mu < 4; mu++) {
       if (!((op->g.comm_mask >> mu) & 1)) continue;
-      comm_stream_write32(g_stream, h->peer[mu][0] + HaloP2P::flag_off(mu, 1), h->seq);
-      comm_stream_write32(g_stream, h->peer[mu][1] + HaloP2P::flag_off(mu, 0), h->seq);
+      comm_stream_write32(cs, h->peer[mu][0] + HaloP2P::flag_off(mu, 1), h->seq);
+      comm_stream_write32(cs, h->peer[mu][1] + HaloP2P::flag_off(mu, 0), h->seq);
     }
+    if (!direct) CUDA_CHECK(cudaEventRecord(g_comm.ev_comm, cs));
     return;
   }
   for (int mu = 1; mu < 4; mu++) {
@@ -351,9 +380,9 @@ void halo_setup(cgptb_fermion_operator* op, const cgptb_lattice* const U[4]) {
     if (g_comm.pgrid[mu] == 1) continue;
     op->g.comm_mask |= 1 << mu;
     size_t bytes = (size_t)(op->g.half4 / op->g.L[mu]) * op->ls() * 12 * real;
-    for (int side = 0; side < 2 && !p2p; side++) {
+    for (int side = 0; side < 2; side++) {
       if (!op->halo_send[mu][side]) CUDA_CHECK(cudaMalloc(&op->halo_send[mu][side], bytes));
-      if (!op->halo_recv[mu][side]) CUDA_CHECK(cudaMalloc(&op->halo_recv[mu][side], bytes));
+      if (!p2p && !op->halo_recv[mu][side]) CUDA_CHECK(cudaMalloc(&op->halo_recv[mu][side], bytes));
     }
     // ghost links: my rank-mu neighbour's high-face U_mu
     FaceGeom fg = make_face(op->g, mu);
@@ -385,6 +414,7 @@ void halo_release(cgptb_fermion_operator* op) {
   if (!op->p2p) return;
   HaloP2P* h = (HaloP2P*)op->p2p;
   cudaStreamSynchronize(g_stream);
+  if (g_comm.stream) cudaStreamSynchronize(g_comm.stream);
   g_arenas.free_list.push_back(std::make_pair(h->arena, h->arena_bytes));
   delete h;
   op->p2p = 0;

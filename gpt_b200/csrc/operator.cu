@@ -63,7 +63,32 @@ __global__ void k_build_links(Geom g, int p, size_t nsitesU, const TU* U0, const
 // the 8-point stencil.  One thread per output (4d site, s); consecutive threads walk s then the 4d site,
 // so the Ls threads of one 4d site broadcast-share its 8 links and spinor reads are 16-byte coalesced.
 // ----------------------------------------------------------------------------------------------------
-template <typename T, bool DAG>
+// [i4][8][9 complex] -> [i4][8][rows 0, 1, f]: f = <d, row 2> / <d, d> with d = conj(row 0 x row 1) (exact for a multiple of an
+// SU(3) matrix, which is what the stencil's link tables hold)
+template <typename T>
+__global__ void k_compress_links(size_t n, const T* __restrict__ links, T* __restrict__ links_c) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // (site, direction)
+  if (i >= n) return;
+  const T* W = links + i * 18;
+  T* o = links_c + i * 14;
+  double w[18];
+  for (int k = 0; k < 18; k++) w[k] = W[k];
+  double nr = 0, ni = 0, dd = 0;
+  for (int c = 0; c < 3; c++) {
+    const int a = (c + 1) % 3, b = (c + 2) % 3;
+    double xr = w[2 * a] * w[6 + 2 * b] - w[2 * a + 1] * w[6 + 2 * b + 1] - (w[2 * b] * w[6 + 2 * a] - w[2 * b + 1] * w[6 + 2 * a + 1]);
+    double xi = w[2 * a] * w[6 + 2 * b + 1] + w[2 * a + 1] * w[6 + 2 * b] - (w[2 * b] * w[6 + 2 * a + 1] + w[2 * b + 1] * w[6 + 2 * a]);
+    // d = conj(x) = (xr, -xi); conj(d) row2 = (xr + i xi)(r + i s)
+    nr += xr * w[12 + 2 * c] - xi * w[12 + 2 * c + 1];
+    ni += xr * w[12 + 2 * c + 1] + xi * w[12 + 2 * c];
+    dd += xr * xr + xi * xi;
+  }
+  for (int k = 0; k < 12; k++) o[k] = W[k];
+  o[12] = dd > 0 ? (T)(nr / dd) : (T)0;
+  o[13] = dd > 0 ? (T)(ni / dd) : (T)0;
+}
+
+template <typename T, bool DAG, bool CMP = false>
 __global__ void __launch_bounds__(128) k_dhop(Geom g, int ls, int p_out, const T* __restrict__ in, size_t in_stride,
                                              T* __restrict__ out, size_t out_stride, const T* __restrict__ links) {
   size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -75,14 +100,14 @@ __global__ void __launch_bounds__(128) k_dhop(Geom g, int ls, int p_out, const T
   T acc[24];
 #pragma unroll
   for (int k = 0; k < 24; k++) acc[k] = 0;
-  hop<0, true, DAG>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
-  hop<0, false, DAG>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
-  hop<1, true, DAG>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
-  hop<1, false, DAG>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
-  hop<2, true, DAG>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
-  hop<2, false, DAG>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
-  hop<3, true, DAG>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
-  hop<3, false, DAG>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
+  hop<0, true, DAG, CMP>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
+  hop<0, false, DAG, CMP>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
+  hop<1, true, DAG, CMP>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
+  hop<1, false, DAG, CMP>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
+  hop<2, true, DAG, CMP>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
+  hop<2, false, DAG, CMP>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
+  hop<3, true, DAG, CMP>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
+  hop<3, false, DAG, CMP>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links);
   store_spinor(out, out_stride, tid, acc);
 }
 
@@ -119,12 +144,18 @@ static void dhop_half(cgptb_fermion_operator* op, bool dag, const cgptb_lattice*
   // split lattice: faces go out first, the interior stencil hides the transfer, then the boundary update
   if (op->g.comm_mask) halo_begin(op, dag, p_out, pin, in->sites);
   if (timed) cudaEventRecord(tev[1], g_stream);
-  if (sizeof(T) == 4 && !use_generic_dhop()) {
+  // two-row link compression: the TMA sweep kernel (single precision) and the generic kernel have a compressed instance
+  if (sizeof(T) == 4 && !use_generic_dhop() && !(op->compress && !dhop_tma_usable(op))) {
     dhop_half_f32(op, dag, (const float*)pin, in->sites, (float*)pout, out->sites, p_out);
   } else {
     int threads = 128;
     unsigned blocks = (unsigned)((half + threads - 1) / threads);
-    if (dag)
+    if (op->compress) {
+      if (dag)
+        k_dhop<T, true, true><<<blocks, threads, 0, g_stream>>>(op->g, ls, p_out, pin, in->sites, pout, out->sites, (const T*)op->links_c[p_out]);
+      else
+        k_dhop<T, false, true><<<blocks, threads, 0, g_stream>>>(op->g, ls, p_out, pin, in->sites, pout, out->sites, (const T*)op->links_c[p_out]);
+    } else if (dag)
       k_dhop<T, true><<<blocks, threads, 0, g_stream>>>(op->g, ls, p_out, pin, in->sites, pout, out->sites, (const T*)op->links[p_out]);
     else
       k_dhop<T, false><<<blocks, threads, 0, g_stream>>>(op->g, ls, p_out, pin, in->sites, pout, out->sites, (const T*)op->links[p_out]);
@@ -938,6 +969,12 @@ static void import_gauge_t(cgptb_fermion_operator* op, const cgptb_lattice* cons
                                                            (const double*)op->ghost_links[1], (const double*)op->ghost_links[2],
                                                            (const double*)op->ghost_links[3]);
     LAUNCH_CHECK();
+    if (op->compress) {
+      const size_t n = (size_t)op->g.half4 * 8;
+      if (!op->links_c[p]) CUDA_CHECK(cudaMalloc(&op->links_c[p], n * 14 * sizeof(T)));
+      k_compress_links<T><<<(unsigned)((n + 127) / 128), 128, 0, g_stream>>>(n, (const T*)op->links[p], (T*)op->links_c[p]);
+      LAUNCH_CHECK();
+    }
   }
   op->has_clover = op->type == CGPTB_WILSON_CLOVER && (op->p.csw_r != 0.0 || op->p.csw_t != 0.0);
   if (op->has_clover) {
@@ -1314,6 +1351,11 @@ int cgptb_create_fermion_operator(cgptb_fermion_operator** out, int optype, int 
   // Wilson-clover with Ls > 0: multi-rhs operator, the fifth dimension enumerates right-hand sides that share the links
   // (wilson_clover(n_rhs=...), lib/gpt/qcd/fermion/wilson.py:134-138)
   op->Ls = params->Ls > 0 ? params->Ls : 0;
+  if (params->link_compression != 0 && params->link_compression != 12) {
+    delete op;
+    CGPTB_ERR("link_compression must be 0 (18 reals per link) or 12 (two rows), got %d", params->link_compression);
+  }
+  op->compress = params->link_compression == 12;
   try {
     if (optype == CGPTB_MOBIUS) {
       if (params->Ls < 1) CGPTB_ERR("mobius needs Ls >= 1");
@@ -1366,6 +1408,7 @@ int cgptb_delete_fermion_operator(cgptb_fermion_operator* op) {
     halo_release(op);
     for (int p = 0; p < 2; p++) {
       if (op->links[p]) cudaFree(op->links[p]);
+      if (op->links_c[p]) cudaFree(op->links_c[p]);
       if (op->clov[p]) cudaFree(op->clov[p]);
       if (op->clov_inv[p]) cudaFree(op->clov_inv[p]);
     }

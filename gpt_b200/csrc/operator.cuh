@@ -23,6 +23,8 @@ struct cgptb_fermion_operator {
   void* links[2] = {0, 0};      // per output parity: [half4][8][9] complex, -c_mu/2 and phases folded in
   void* links_pad[2] = {0, 0};  // the same links as [2 halves][site][304 B] for the TMA sweep kernel (dslash_tma.cu), built lazily
   bool links_pad_valid = false;
+  bool compress = false;        // two-row link compression (cgptb_fermion_params::link_compression == 12)
+  void* links_c[2] = {0, 0};    // per output parity: [half4][8][rows 0 and 1 (12 reals), U(1) factor f (2 reals)]
   bool open_bc = false;         // boundary_phases[3] == 0: results vanish on the global time slices 0 and T-1
   bool has_clover = false;
   void* clov[2] = {0, 0};       // per parity: [72][half4] reals

@@ -26,7 +26,8 @@ class mobius_class_operator(fine_operator):
         return g.propagator_operator(op)
 
 
-@g.params_convention(mass=None, mass_plus=None, mass_minus=None, b=None, c=None, M5=None, boundary_phases=None, Ls=None)
+@g.params_convention(mass=None, mass_plus=None, mass_minus=None, b=None, c=None, M5=None, boundary_phases=None, Ls=None,
+                     link_compression=None)  # link_compression: extension of this package (12 = two-row SU(3) links)
 def mobius(U, params):
     params = copy.deepcopy(params)
     return mobius_class_operator("mobius", U, params, otype=g.ot_vector_spin_color(4, 3))
@@ -45,7 +46,8 @@ class zmobius_class_operator(mobius_class_operator):
         return g.matrix_operator(mat=mat, adj_mat=adj_mat, inv_mat=inv_mat, adj_inv_mat=adj_inv_mat, vector_space=self.vector_space_F_eo)
 
 
-@g.params_convention(omega=None, mass=None, mass_plus=None, mass_minus=None, b=None, c=None, M5=None, boundary_phases=None)
+@g.params_convention(omega=None, mass=None, mass_plus=None, mass_minus=None, b=None, c=None, M5=None, boundary_phases=None,
+                     link_compression=None)
 def zmobius(U, params):
     """g.qcd.fermion.zmobius (lib/gpt/qcd/fermion/zmobius.py:62-74): Moebius with complex, s-dependent coefficients
     b_s, c_s = 1/2 ((b + c) / omega_s +- (b - c)); Ls = len(omega)"""

@@ -8,6 +8,7 @@ from gpt_b200.qcd.fermion.operator import fine_operator
 @g.params_convention(
     kappa=None, mass=None, cF=1, use_legacy=False, boundary_phases=None, isAnisotropic=None,
     csw_r=None, csw_t=None, nu=None, xi_0=None, n_rhs=1,
+    link_compression=None,  # extension of this package: 12 = two-row SU(3) link compression in the stencil's link tables
 )
 def wilson_clover(U, params):
     params = copy.deepcopy(params)
@@ -27,7 +28,7 @@ def wilson_clover(U, params):
     return fine_operator("wilson_clover", U, params, otype=g.ot_vector_spin_color(4, 3))
 
 
-@g.params_convention(mass=None, mu=None, boundary_phases=None)
+@g.params_convention(mass=None, mu=None, boundary_phases=None, link_compression=None)
 def wilson_twisted_mass(U, params):
     """g.qcd.fermion.wilson_twisted_mass (lib/gpt/qcd/fermion/wilson.py:99-107): Wilson hopping term with the site-diagonal
     term (4 + mass) + i mu gamma_5; isotropic, no clover term"""

@@ -152,6 +152,10 @@ typedef struct {
   /* zmobius (lib/cgpt/lib/operators/zmobius.h:20-56): n_omega = Ls complex omega_s (re,im); 0 = plain Moebius */
   int n_omega;
   double omega[2 * 64];
+  /* extension (no counterpart in the reference's parameter tables): 12 = keep only the first two rows of every SU(3) link in
+     the stencil's link tables and rebuild the third in registers (row_2 = f conj(row_0 x row_1), f = the U(1) factor the stored
+     link carries: -c_mu/2 and the boundary phase); 0 = all 18 reals */
+  int link_compression;
 } cgptb_fermion_params;
 
 /* cgpt.create_fermion_operator(optype, prec, params): U = 4 colour-matrix lattices on the full 4d grid */
@@ -177,6 +181,22 @@ int cgptb_lattice_spin_matrix(cgptb_lattice* d, const cgptb_lattice* s, const do
 /* gpt.scale_per_coordinate(d, s, a, dim) (lib/gpt/core/transform.py:210-214, cgpt.lattice_scale_per_coordinate): d = a[x_dim] s,
    a = n complex factors (re,im), dim counts the fifth dimension as 0 on 5d lattices */
 int cgptb_lattice_scale_per_coordinate(cgptb_lattice* d, const cgptb_lattice* s, const double* a_re_im, int n, int dim);
+
+/* ---- generic matrix-vector stencils: cgpt.stencil_matrix_vector_create / _execute / _delete
+   (lib/cgpt/lib/stencil.cc:41-58,101-121 and stencil/matrix_vector.h:20-290; used by benchmarks/stencil.py:91-145 and
+   tests/core/stencil.py:168-215).  points = n_points shifts of 4 ints; code line i = code_ints[5 i ..] = (target, accumulate
+   or -1, source, source_point, number of factors) with weight (re, im); its factors follow each other in `factors` as
+   (matrix field index, point, adjoint) and are applied right to left:
+     vector[target](x) = weight M_1 ... M_n vector[source](x + p_source) [+ vector[accumulate](x)].
+   Lines of a block of code_parallel_block_size run in order, blocks are independent.  Colour-matrix and (spin-)colour-vector
+   fields on the full 4d lattice of one rank.                                                               */
+typedef struct cgptb_stencil_mv cgptb_stencil_mv;
+int cgptb_stencil_matrix_vector_create(cgptb_stencil_mv** out, const int dims4[4], int precision, int n_points, const int* points,
+                                       int n_code, const int* code_ints, const double* weights_re_im, const int* factors,
+                                       int code_parallel_block_size, int local, int matrix_parity, int vector_parity);
+int cgptb_stencil_matrix_vector_execute(cgptb_stencil_mv* s, const cgptb_lattice* const* matrix_fields, int n_m,
+                                        cgptb_lattice* const* vector_fields, int n_v, int fast_osites);
+int cgptb_stencil_matrix_vector_delete(cgptb_stencil_mv* s);
 
 /* ---- random numbers: cgpt.create_random(engine, seed) / cgpt.random_sample(rng, params) / cgpt.delete_random
    (lib/cgpt/lib/random.cc:38-101, random/engine.h:64-125).  Same streams as the reference: RANLUX24 lanes seeded by

@@ -951,3 +951,131 @@ def test_open_bc_dhop_host_and_long_linear_combination(g, fields):
     dst = vs[9]
     g.cgpt.lattice_lc(dst.obj, False, c, [v.obj for v in vs])
     assert rel(dst[:], want) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------------
+# two-row SU(3) link compression (an option of this package: params link_compression=12): the stencil's link tables keep rows
+# 0 and 1 and the U(1) factor of the stored link (-c_mu/2 x boundary phase); row 2 is rebuilt in registers.  Against the
+# 18-real path and the oracle, for the TMA sweep kernel (single, Ls % 4 == 0), the generic kernel (double; single where the
+# sweep kernel does not apply), complex boundary phases, anisotropy and open boundary conditions (vanishing links)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["double", "single"])
+def test_link_compression(g, fields, precision):
+    prec = prec_of(g, precision)
+    tol = TOL[precision]
+    close = 1e-13 if precision == "double" else 3e-6  # compressed against uncompressed: rounding of the rebuilt row only
+    grid = g.grid(DIMS, prec)
+    cdt = prec.complex_dtype
+    U = fields["U"]
+    Ug = to_links(g, grid, U)
+    Uo = [u.astype(cdt) for u in U]
+    phases = [1.0, -1.0, np.exp(0.3j), -1.0]
+    # Moebius: every opcode that contains the stencil
+    for Ls in (8, 6):
+        params = dict(mass=0.08, M5=1.8, b=1.5, c=0.5, Ls=Ls, boundary_phases=phases)
+        m18 = g.qcd.fermion.mobius(Ug, dict(params))
+        m12 = g.qcd.fermion.mobius(Ug, dict(params, link_compression=12))
+        mo = qcd.mobius(Uo, **params)
+        s5 = oracle_random("cmp" + str(Ls)).cnormal([Ls] + DIMS, (4, 3)).astype(cdt)
+        src = to_spinor(g, m18.F_grid, s5)
+        for tag, a, b, ref in [("Dhop", m12.Dhop, m18.Dhop, mo.Dhop(s5)), ("DhopDag", m12.Dhop.adj(), m18.Dhop.adj(), mo.Dhop(s5, dag=True)),
+                               ("M", m12, m18, mo.M(s5)), ("Mdag", m12.adj(), m18.adj(), mo.Mdag(s5))]:
+            got = from_spinor(g(a * src), s5)
+            assert rel(got, ref) < tol, (Ls, tag)
+            assert rel(got, from_spinor(g(b * src), s5)) < close, (Ls, tag)
+        e = qcd.eo_ops(mo)
+        for cb in (g.even, g.odd):
+            half = to_spinor(g, m12.F_grid_eo, s5, cb)
+            out = from_spinor(g(m12.Meooe * half), s5)
+            assert rel(out, e.Meooe(e.proj(s5, cb.tag), cb.tag)) < tol
+    # Wilson-clover: anisotropic with a clover term, and open boundary conditions in time
+    s4 = fields["src4"].astype(cdt)
+    src4 = to_spinor(g, grid, s4)
+    for p in (dict(CLOVER, boundary_phases=phases),
+              dict(kappa=0.135, csw_r=1.978, csw_t=1.978, cF=1.3, xi_0=1, nu=1, isAnisotropic=False, boundary_phases=[1.0, 1.0, 1.0, 0.0])):
+        w18 = g.qcd.fermion.wilson_clover(Ug, dict(p))
+        w12 = g.qcd.fermion.wilson_clover(Ug, dict(p, link_compression=12))
+        wo = qcd.wilson_clover(Uo, **p)
+        for tag, a, b, ref in [("M", w12, w18, wo.M(s4)), ("Mdag", w12.adj(), w18.adj(), wo.Mdag(s4)), ("Dhop", w12.Dhop, w18.Dhop, wo.Dhop(s4))]:
+            got = from_spinor(g(a * src4), s4)
+            assert rel(got, ref) < tol, tag
+            assert rel(got, from_spinor(g(b * src4), s4)) < close, tag
+    # a solve on the compressed operator: same iteration count as on the 18-real one
+    if precision == "double":
+        params = dict(mass=0.1, M5=1.8, b=1.5, c=0.5, Ls=8, boundary_phases=[1.0, 1.0, 1.0, -1.0])
+        inv = g.algorithms.inverter
+        pc = g.qcd.fermion.preconditioner
+        s5 = oracle_random("cmp solve").cnormal([8] + DIMS, (4, 3))
+        its = []
+        sols = []
+        for extra in ({}, {"link_compression": 12}):
+            m = g.qcd.fermion.mobius(Ug, dict(params, **extra))
+            cg = inv.cg(eps=1e-8, maxiter=500)
+            sols.append(g(inv.preconditioned(pc.eo2_ne(), cg)(m) * to_spinor(g, m.F_grid, s5))[:])
+            its.append(len(cg.history))
+        assert its[0] == its[1] and rel(sols[1], sols[0]) < 1e-9
+    with pytest.raises(Exception):
+        g.qcd.fermion.mobius(Ug, dict(mass=0.1, M5=1.8, b=1.5, c=0.5, Ls=8, boundary_phases=phases, link_compression=8))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# generic matrix-vector stencil (cgpt.stencil_matrix_vector_*): the covariant Laplacian of
+# /root/reference/benchmarks/stencil.py:91-119 (eight one-link terms, links and pre-shifted adjoint links as separate matrix
+# fields), the three-point version of tests/core/stencil.py:168-215 (adjoint flag + shifted matrix point), a two-link term with a
+# diagonal shift and two independent code blocks -- against numpy on the oracle's fields
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["double", "single"])
+def test_stencil_matrix_vector(g, fields, precision):
+    prec = prec_of(g, precision)
+    tol = TOL[precision]
+    cdt = prec.complex_dtype
+    grid = g.grid(DIMS, prec)
+    U = [u.astype(cdt) for u in fields["U"]]
+    Ug = to_links(g, grid, fields["U"])
+    s4 = fields["src4"].astype(cdt)
+    src = to_spinor(g, grid, s4)
+
+    def mul(m, f):
+        return np.einsum("...ab,...sb->...sa", m, f)
+
+    evec = [(1, 0, 0, 0), (0, 1, 0, 0), (0, 0, 1, 0), (0, 0, 0, 1)]
+    nevec = [tuple(-x for x in y) for y in evec]
+    # (a) benchmarks/stencil.py: laplace with U and UdagShift = adj(cshift(U, mu, -1)) as eight matrix fields
+    Udag = [qcd.adj(qcd.shift(U[mu], mu, -1)) for mu in range(4)]
+    Udag_g = to_links(g, grid, Udag)
+    _X, _Xp, _Xm = 0, [1, 2, 3, 4], [5, 6, 7, 8]
+    code = [(0, 1, _X, -1, -8.0, [])]
+    for mu in range(4):
+        code.append((0, 1, _Xp[mu], 0, 1.0, [(mu, _X, 0)]))
+        code.append((0, 1, _Xm[mu], 0, 1.0, [(4 + mu, _X, 0)]))
+    st = g.stencil.matrix_vector(Ug[0], src, [(0, 0, 0, 0)] + evec + nevec, code)
+    dst = g.lattice(src)
+    st(Ug + Udag_g, [dst, src])
+    ref = -8.0 * s4
+    for mu in range(4):
+        ref = ref + mul(U[mu], qcd.shift(s4, mu, +1)) + mul(Udag[mu], qcd.shift(s4, mu, -1))
+    assert rel(from_spinor(dst, s4), ref) < tol
+    # (b) tests/core/stencil.py: the backward term through the adjoint flag and a shifted matrix point
+    for mu in range(4):
+        st = g.stencil.matrix_vector(Ug[0], src, [(0, 0, 0, 0), evec[mu], nevec[mu]], [
+            {"target": 0, "source": 1, "source_point": 0, "accumulate": -1, "weight": -2.0, "factor": []},
+            {"target": 0, "source": 1, "source_point": 1, "accumulate": 0, "weight": 1.0, "factor": [(mu, 0, 0)]},
+            {"target": 0, "source": 1, "source_point": 2, "accumulate": 0, "weight": 1.0, "factor": [(mu, 2, 1)]},
+        ])
+        st(Ug, [dst, src])
+        ref = -2.0 * s4 + mul(U[mu], qcd.shift(s4, mu, +1)) + mul(Udag[mu], qcd.shift(s4, mu, -1))
+        assert rel(from_spinor(dst, s4), ref) < tol, mu
+    # (c) two factors, a diagonal point, a complex weight, and two independent blocks writing two targets
+    diag = (1, 0, -1, 0)
+    st = g.stencil.matrix_vector(Ug[0], src, [(0, 0, 0, 0), evec[0], diag, evec[3]], [
+        (0, 2, 2, -1, 0.5 - 0.25j, [(0, 0, 0), (2, 1, 1)]),   # dst0(x) = w U_0(x) U_2^dag(x + 0) src(x + diag)
+        (1, 2, 3, 2, 2.0, [(3, 0, 0)]),                         # dst1(x) = 2 U_3(x) src(x + t) + src(x)
+    ], code_parallel_block_size=1)
+    d0, d1 = g.lattice(src), g.lattice(src)
+    st(Ug, [d0, d1, src])
+    sd = qcd.shift(qcd.shift(s4, 0, +1), 2, -1)
+    ref0 = (0.5 - 0.25j) * mul(U[0], mul(qcd.adj(qcd.shift(U[2], 0, +1)), sd))
+    ref1 = 2.0 * mul(U[3], qcd.shift(s4, 3, +1)) + s4
+    assert rel(from_spinor(d0, s4), ref0) < tol and rel(from_spinor(d1, s4), ref1) < tol
+    with pytest.raises(Exception):
+        g.stencil.matrix_vector(Ug[0], src, [(0, 0, 0, 0)], [(0, 1, 0, -1, 1.0, []), (0, 1, 0, -1, 1.0, [])], code_parallel_block_size=3)
