@@ -95,6 +95,7 @@ SIGNATURES = {
     "cgptb_linear_combination": (c_int, [_pp, c_int, _pp, c_int, _pd]),
     "cgptb_lattice_scale": (c_int, [c_void_p, c_double, c_double]),
     "cgptb_lattice_slice_inner_product": (c_int, [c_void_p, c_void_p, _pd]),
+    "cgptb_debug_tma_schedule": (c_int, [_pi, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _pi, c_int, _pi]),
     "cgptb_stencil_matrix_vector_create": (c_int, [_pp, _pi, c_int, c_int, _pi, c_int, _pi, _pd, _pi, c_int, c_int, c_int, c_int]),
     "cgptb_stencil_matrix_vector_execute": (c_int, [c_void_p, _pp, c_int, _pp, c_int, c_int]),
     "cgptb_stencil_matrix_vector_delete": (c_int, [c_void_p]),
@@ -357,6 +358,20 @@ def lattice_slice_inner_product(b, a, nt):
     out = np.zeros(nt, dtype=np.complex128)
     _check(_lib_ready().cgptb_lattice_slice_inner_product(c_void_p(b), c_void_p(a), out.ctypes.data_as(_pd)))
     return out
+
+
+def debug_tma_schedule(dims4, Ls, grid, chunks_per_cta=1, sched=1, trl=16, t_begin=0, t_count=0):
+    """work items of the TMA sweep kernel: array [n, 6] = (group, xh0, y0, z0, t0, trl); needs no GPU"""
+    d = (c_int * 4)(*[int(x) for x in dims4])
+    cap = 1 << 16
+    out = np.zeros((cap, 6), dtype=np.int32)
+    n = c_int()
+    lib = library()
+    if lib.cgptb_debug_tma_schedule(d, int(Ls), int(grid), int(chunks_per_cta), int(sched), int(trl), int(t_begin), int(t_count),
+                                    out.ctypes.data_as(_pi), cap, ctypes.byref(n)):
+        raise RuntimeError(lib.cgptb_last_error().decode())
+    assert n.value <= cap
+    return out[: n.value].copy()
 
 
 # ---- generic matrix-vector stencil ---------------------------------------------------------------------------

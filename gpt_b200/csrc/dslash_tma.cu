@@ -833,3 +833,41 @@ void dhop_half_f32_tma(cgptb_fermion_operator* op, bool dag, const float* pin, s
 }
 
 }  // namespace cgptb
+
+// the work schedule of the TMA sweep kernel as a table (host only; tests/test_cpu_boundary.py checks that every (tile, chunk
+// group, time slice) is covered exactly once): item i = (group, x/2 origin, y origin, z origin, first slice, number of slices)
+extern "C" int cgptb_debug_tma_schedule(const int dims4[4], int Ls, int grid, int chunks_per_cta, int sched, int trl, int t_begin,
+                                        int t_count, int* out6, int max_items, int* n_items) {
+  using namespace cgptb;
+  using namespace cgptb::tma;
+  CGPTB_API_BEGIN
+  if (chunks_per_cta < 1 || dims4[0] % (2 * TX) || dims4[1] % TY || dims4[2] % TZ || Ls % SC || (Ls / SC) % chunks_per_cta || grid < 1)
+    CGPTB_ERR("lattice %d.%d.%d.%d Ls=%d is not tiled by the sweep kernel with %d chunks per CTA", dims4[0], dims4[1], dims4[2], dims4[3], Ls, chunks_per_cta);
+  Geo G;
+  memset(&G, 0, sizeof(G));
+  G.hx = dims4[0] / 2;
+  G.Ly = dims4[1];
+  G.Lz = dims4[2];
+  G.T = dims4[3];
+  G.nbx = G.hx / TX;
+  G.nby = G.Ly / TY;
+  G.nbz = G.Lz / TZ;
+  G.ngroup = Ls / SC / chunks_per_cta;
+  if (t_count <= 0) {
+    t_begin = 0;
+    t_count = G.T;
+  }
+  std::vector<ItemDesc> items = build_schedule(G, grid, t_begin, t_count, sched, trl);
+  *n_items = (int)items.size();
+  for (int i = 0; i < (int)items.size() && i < max_items; i++) {
+    const ItemDesc& it = items[i];
+    int* o = out6 + 6 * i;
+    o[0] = it.c;
+    o[1] = it.xh0;
+    o[2] = it.y0;
+    o[3] = it.z0;
+    o[4] = it.t0;
+    o[5] = it.trl;
+  }
+  CGPTB_API_END
+}

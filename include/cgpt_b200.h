@@ -182,6 +182,11 @@ int cgptb_lattice_spin_matrix(cgptb_lattice* d, const cgptb_lattice* s, const do
    a = n complex factors (re,im), dim counts the fifth dimension as 0 on 5d lattices */
 int cgptb_lattice_scale_per_coordinate(cgptb_lattice* d, const cgptb_lattice* s, const double* a_re_im, int n, int dim);
 
+/* work schedule of the TMA sweep kernel (gpt_b200/csrc/dslash_tma.cu) as a table, host only: item i = out6[6 i ..] = (chunk group,
+   x/2 origin, y origin, z origin, first time slice, number of time slices); item i runs on CTA i % grid.  For tests / tuning. */
+int cgptb_debug_tma_schedule(const int dims4[4], int Ls, int grid, int chunks_per_cta, int sched, int trl, int t_begin, int t_count,
+                             int* out6, int max_items, int* n_items);
+
 /* ---- generic matrix-vector stencils: cgpt.stencil_matrix_vector_create / _execute / _delete
    (lib/cgpt/lib/stencil.cc:41-58,101-121 and stencil/matrix_vector.h:20-290; used by benchmarks/stencil.py:91-145 and
    tests/core/stencil.py:168-215).  points = n_points shifts of 4 ints; code line i = code_ints[5 i ..] = (target, accumulate
