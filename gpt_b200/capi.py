@@ -164,6 +164,11 @@ def set_stream(cuda_stream):
     _check(_lib_ready().cgptb_set_stream(c_void_p(cuda_stream)))
 
 
+def get_stream():
+    """the CUDA stream the library launches on (a cudaStream_t as an integer), e.g. for torch.cuda.ExternalStream"""
+    return int(_lib_ready().cgptb_get_stream() or 0)
+
+
 def timer_start():
     _check(_lib_ready().cgptb_timer_start())
 

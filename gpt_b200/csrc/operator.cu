@@ -111,6 +111,56 @@ __global__ void __launch_bounds__(128) k_dhop(Geom g, int ls, int p_out, const T
   store_spinor(out, out_stride, tid, acc);
 }
 
+// The same stencil with one WARP per hop direction: a CTA of 8 warps handles 32 consecutive output sites, warp d computes the
+// hop in direction d for all of them (no divergence: the direction is uniform in a warp; neighbour spinors of consecutive sites
+// are consecutive), the eight partial spinors meet in shared memory and 3 (fp32) / 6 (fp64) x 32 threads add them up and store
+// aligned 32-byte blocks.  Eight times the threads of k_dhop and eight independent loads in flight per site: what a small or
+// single-rhs lattice (Wilson Ls = 1: 32 k sites per parity at 16^4) needs to hide the latency of its loads.
+template <typename T, bool DAG, bool CMP>
+__global__ void __launch_bounds__(256) k_dhop_dir(Geom g, int ls, int p_out, const T* __restrict__ in, size_t in_stride,
+                                                  T* __restrict__ out, size_t out_stride, const T* __restrict__ links) {
+  __shared__ T part[8 * 24 * 32];  // [direction][component][site of the CTA]
+  const int lane = threadIdx.x & 31, d = threadIdx.x >> 5;
+  const size_t nsite = (size_t)g.half4 * ls;
+  const size_t tid = (size_t)blockIdx.x * 32 + lane;
+  T acc[24];
+#pragma unroll
+  for (int k = 0; k < 24; k++) acc[k] = 0;
+  if (tid < nsite) {
+    const int i4 = (int)(tid / ls);
+    const int s = (int)(tid - (size_t)i4 * ls);
+    int x, y, z, t;
+    cb_coords(g, p_out, i4, x, y, z, t);
+    switch (d) {  // uniform in the warp
+      case 0: hop<0, true, DAG, CMP>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links); break;
+      case 1: hop<0, false, DAG, CMP>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links); break;
+      case 2: hop<1, true, DAG, CMP>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links); break;
+      case 3: hop<1, false, DAG, CMP>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links); break;
+      case 4: hop<2, true, DAG, CMP>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links); break;
+      case 5: hop<2, false, DAG, CMP>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links); break;
+      case 6: hop<3, true, DAG, CMP>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links); break;
+      default: hop<3, false, DAG, CMP>(acc, g, x, y, z, t, i4, s, ls, in, in_stride, links); break;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 24; k++) part[(d * 24 + k) * 32 + lane] = acc[k];
+  __syncthreads();
+  constexpr int RB = 32 / sizeof(T);      // reals per 32-byte block: 8 / 4
+  constexpr int NBLK = 24 / RB;           // blocks per spinor: 3 / 6
+  if (threadIdx.x < NBLK * 32 && tid < nsite) {
+    const int kb = threadIdx.x >> 5;      // (kb, lane): warps 0 .. NBLK-1
+    T v[RB];
+#pragma unroll
+    for (int e = 0; e < RB; e++) {
+      T sum = part[(0 * 24 + kb * RB + e) * 32 + lane];
+#pragma unroll
+      for (int dd = 1; dd < 8; dd++) sum += part[(dd * 24 + kb * RB + e) * 32 + lane];
+      v[e] = sum;
+    }
+    st256(out + ((size_t)kb * out_stride + tid) * RB, v);
+  }
+}
+
 void dhop_half_f32(cgptb_fermion_operator* op, bool dag, const float* pin, size_t in_stride, float* pout, size_t out_stride,
                    int p_out);  // dslash_f32.cu
 
@@ -145,12 +195,30 @@ static void dhop_half(cgptb_fermion_operator* op, bool dag, const cgptb_lattice*
   if (op->g.comm_mask) halo_begin(op, dag, p_out, pin, in->sites);
   if (timed) cudaEventRecord(tev[1], g_stream);
   // two-row link compression: the TMA sweep kernel (single precision) and the generic kernel have a compressed instance
-  if (sizeof(T) == 4 && !use_generic_dhop() && !(op->compress && !dhop_tma_usable(op))) {
+  static int dir_env = getenv("CGPTB_DHOP_DIR") ? atoi(getenv("CGPTB_DHOP_DIR")) : -1;
+  // one warp per hop direction (k_dhop_dir): measured SLOWER than one thread per site for single-rhs Wilson-clover at 16^4 and at
+  // 32^3 x 64 in both precisions (profiles/ablation_r2.txt), so it only runs on request (CGPTB_DHOP_DIR=1)
+  const bool use_dir = dir_env == 1 && !dhop_tma_usable(op);
+  if (sizeof(T) == 4 && !use_generic_dhop() && !use_dir && !(op->compress && !dhop_tma_usable(op))) {
     dhop_half_f32(op, dag, (const float*)pin, in->sites, (float*)pout, out->sites, p_out);
   } else {
     int threads = 128;
     unsigned blocks = (unsigned)((half + threads - 1) / threads);
-    if (op->compress) {
+    if (use_dir) {
+      const unsigned db = (unsigned)((half + 31) / 32);
+      const T* lk = (const T*)(op->compress ? op->links_c[p_out] : op->links[p_out]);
+#define DIR_LAUNCH(DAG_, CMP_) k_dhop_dir<T, DAG_, CMP_><<<db, 256, 0, g_stream>>>(op->g, ls, p_out, pin, in->sites, pout, out->sites, lk)
+      if (op->compress) {
+        if (dag)
+          DIR_LAUNCH(true, true);
+        else
+          DIR_LAUNCH(false, true);
+      } else if (dag)
+        DIR_LAUNCH(true, false);
+      else
+        DIR_LAUNCH(false, false);
+#undef DIR_LAUNCH
+    } else if (op->compress) {
       if (dag)
         k_dhop<T, true, true><<<blocks, threads, 0, g_stream>>>(op->g, ls, p_out, pin, in->sites, pout, out->sites, (const T*)op->links_c[p_out]);
       else

@@ -348,7 +348,12 @@ static void sample_grid(GridRng& G, int nel, int dist, double p0, double p1, TO*
 }
 
 static void lattice_geometry(const cgptb_lattice* l, int& nd, int ldims[5], int gdims[5], int lstart[5]) {
-  if (l->cb != CGPTB_FULL) CGPTB_ERR("random: only full (not checkerboarded) lattices can be sampled");
+  // A checkerboarded lattice is sampled like the reference samples a GridRedBlackCartesian (lib/cgpt/lib/random/parallel.h:
+  // 27-128): the generators' blocks and the fill order follow the REDUCED coordinates (x/2, y, z, t) -- _ldimensions and
+  // _gdimensions of such a grid have the checkerboarded extent halved --, whatever parity the lattice is labelled with; the
+  // sample of reduced site (x/2, y, z, t) lands on the stored site with that x/2, which is this library's half-lattice order.
+  const bool half = l->cb != CGPTB_FULL;
+  if (half && (l->dims4[0] / 2) % 2) CGPTB_ERR("random: a checkerboarded lattice needs an x extent that is a multiple of 4 (2^4 blocks of the reduced lattice)");
   nd = 0;
   if (l->Ls > 0) {
     ldims[0] = gdims[0] = l->Ls;
@@ -356,9 +361,10 @@ static void lattice_geometry(const cgptb_lattice* l, int& nd, int ldims[5], int 
     nd = 1;
   }
   for (int mu = 0; mu < 4; mu++, nd++) {
-    ldims[nd] = l->dims4[mu];
-    gdims[nd] = l->dims4[mu] * g_comm.pgrid[mu];
-    lstart[nd] = l->dims4[mu] * g_comm.pcoor[mu];
+    const int d = half && mu == 0 ? l->dims4[mu] / 2 : l->dims4[mu];
+    ldims[nd] = d;
+    gdims[nd] = d * g_comm.pgrid[mu];
+    lstart[nd] = d * g_comm.pcoor[mu];
   }
 }
 

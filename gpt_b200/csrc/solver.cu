@@ -22,6 +22,8 @@ void dhop_half_f32_fused(cgptb_fermion_operator* op, bool dag, const float* pin,
 bool sweep_supported(int ls);  // sweep.cu
 bool op_cg_update_sweep(cgptb_fermion_operator* op, double a, double b, cgptb_lattice* p, const cgptb_lattice* r, cgptb_lattice* psi,
                         cgptb_lattice* t);
+bool op_s_sweep_sub_dot(cgptb_fermion_operator* op, int mode, const cgptb_lattice* in, const cgptb_lattice* z, cgptb_lattice* out,
+                        const cgptb_lattice* dotp, double* dot);
 void blas_finalize(int nblocks, int ncomp, const double* partial, double* host_out);  // blas.cu
 double* blas_partial_scratch(int nblocks);
 
@@ -66,19 +68,24 @@ void op_schur_two(cgptb_fermion_operator* op, bool dag, const cgptb_lattice* in,
         done_dot = true;
       }
     } else {
-      // Meooe MooeeInv = Dhop o T applied as one register-resident sweep + the plain stencil
+      // Meooe MooeeInv = Dhop o T applied as one register-resident sweep + the plain stencil (the TMA sweep kernel where it
+      // applies: decomposed lattices, compressed links); the last sweep of Mpc^dag subtracts from x and accumulates <p, A p>
       if (!dag) {
-        op_s_sweep(op, SWEEP_T, in, td);
+        if (t_in)
+          td = const_cast<cgptb_lattice*>(t_in);
+        else
+          op_s_sweep(op, SWEEP_T, in, td);
         op_dhop(op, false, td, tc0);
         op_s_sweep(op, SWEEP_T, tc0, tc1);
         op_dhop(op, false, tc1, out);
+        blas_axpy(out, -1.0, 0.0, out, in);
       } else {
         op_dhop(op, true, in, tc0);
         op_s_sweep(op, SWEEP_TDAG, tc0, tc1);
         op_dhop(op, true, tc1, td);
-        op_s_sweep(op, SWEEP_TDAG, td, out);
+        if (!op_s_sweep_sub_dot(op, SWEEP_TDAG, td, in, out, dotp, dot)) CGPTB_ERR("sweep kernel missing for Ls=%d", op->Ls);
+        if (dot) done_dot = true;
       }
-      blas_axpy(out, -1.0, 0.0, out, in);
     }
   } else {
     if (!dag) {
@@ -132,7 +139,8 @@ int cgptb_cg_eo2_ne(cgptb_fermion_operator* op, cgptb_lattice* psi, const cgptb_
     }
   } guard{all};
   static int no_upd = getenv("CGPTB_NO_FUSED_UPDATE") ? 1 : 0;
-  bool fuse_update = !no_upd && !op->zmobius && dhop_fusable(op) && sweep_supported(op->Ls);
+  static int no_sweep_cg = getenv("CGPTB_NO_SWEEP") ? 1 : 0;
+  bool fuse_update = !no_upd && !no_sweep_cg && op->type == CGPTB_MOBIUS && !op->zmobius && sweep_supported(op->Ls);
   for (int i = 0; i < (fuse_update ? 5 : 4); i++)
     if (cgptb_create_lattice(all[i], op->dims4, op->Ls, op->prec, CGPTB_OT_VSPINCOLOR, src->cb)) CGPTB_ERR("%s", cgptb_last_error());
 

@@ -18,6 +18,18 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
 }
 
+// d[0..1] += conj(a) * b summed over the complex numbers of a 16-byte unit, d[2] += |b|^2, in double
+__device__ __forceinline__ void vdot_acc(float4 a, float4 b, double (&d)[3]) {
+  d[0] += (double)a.x * b.x + (double)a.y * b.y + (double)a.z * b.z + (double)a.w * b.w;
+  d[1] += (double)a.x * b.y - (double)a.y * b.x + (double)a.z * b.w - (double)a.w * b.z;
+  d[2] += (double)b.x * b.x + (double)b.y * b.y + (double)b.z * b.z + (double)b.w * b.w;
+}
+__device__ __forceinline__ void vdot_acc(double2 a, double2 b, double (&d)[3]) {
+  d[0] += a.x * b.x + a.y * b.y;
+  d[1] += a.x * b.y - a.y * b.x;
+  d[2] += b.x * b.x + b.y * b.y;
+}
+
 // CG vector update fused in front of the sweep (cg.py:91-95 + the first factor of the next matrix application):
 //   psi += a p ; p = b p + r ; out = T p         (in = p is updated in place)
 template <typename T>
@@ -28,9 +40,19 @@ struct UpdateArgs {
   T* p;
 };
 
-template <typename T, int LS, int NSB, bool UPD>
+// Epilogue behind the sweep (the last factor of Mpc^dag inside CG, schur_complement_two.py:100-112 + cg.py:83):
+//   out = z - S in ; partial[cta] = (re, im) <dotp, out>, |out|^2 in double
+template <typename T>
+struct SubDotArgs {
+  const T* z;
+  const T* dotp;   // may be 0: no reduction
+  double* partial; // [ctas][3]
+};
+
+template <typename T, int LS, int NSB, bool UPD, bool EPI = false>
 __global__ void __launch_bounds__(NSB* VecOf<T>::NB, 2) k_s_sweep(size_t n4, const T* __restrict__ in, T* __restrict__ out,
-                                                               size_t stride, SweepParams<T> P, int ntiles, UpdateArgs<T> upd) {
+                                                               size_t stride, SweepParams<T> P, int ntiles, UpdateArgs<T> upd,
+                                                               SubDotArgs<T> epi = SubDotArgs<T>()) {
   typedef typename VecOf<T>::type V;
   constexpr int NB = VecOf<T>::NB;
   constexpr int PITCH = LS + 1;  // vectors per (block, site) row in shared memory: conflict-free column reads
@@ -56,6 +78,7 @@ __global__ void __launch_bounds__(NSB* VecOf<T>::NB, 2) k_s_sweep(size_t n4, con
     asm volatile("cp.async.commit_group;");
   };
 
+  double dsum[3] = {0.0, 0.0, 0.0};
   int tile = blockIdx.x;
   if (tile < ntiles) prefetch(tile, sm);
   int cur = 0;
@@ -128,9 +151,26 @@ __global__ void __launch_bounds__(NSB* VecOf<T>::NB, 2) k_s_sweep(size_t n4, con
       int kb = q / (NSB * LS), rem = q - kb * (NSB * LS);
       int k = 2 * kb + half;
       int l = rem / LS, s = rem - l * LS;
-      if (l < nloc) __stcs(gout + (((size_t)kb * stride + site0 * LS + rem) << 1) + half, buf[(k * NSB + l) * PITCH + s]);
+      if (l < nloc) {
+        const size_t o = (((size_t)kb * stride + site0 * LS + rem) << 1) + half;
+        V r = buf[(k * NSB + l) * PITCH + s];
+        if (EPI) {
+          r = vfma((T)-1, r, __ldcs(reinterpret_cast<const V*>(epi.z) + o));
+          if (epi.dotp) vdot_acc(__ldcs(reinterpret_cast<const V*>(epi.dotp) + o), r, dsum);
+        }
+        __stcs(gout + o, r);
+      }
     }
     __syncthreads();  // buf is refilled by the prefetch of the next iteration
+  }
+  if (EPI && epi.dotp) {
+    __shared__ double red[96];
+    block_reduce<3>(dsum, red);
+    if (threadIdx.x == 0) {
+      epi.partial[blockIdx.x * 3 + 0] = dsum[0];
+      epi.partial[blockIdx.x * 3 + 1] = dsum[1];
+      epi.partial[blockIdx.x * 3 + 2] = dsum[2];
+    }
   }
 }
 
@@ -142,22 +182,48 @@ constexpr int sweep_nsb() {
   return n;
 }
 
-template <typename T, int LS, bool UPD>
-static void launch_sweep(size_t n4, const T* in, T* out, size_t stride, const SweepParams<T>& P, const UpdateArgs<T>& upd) {
+template <typename T, int LS>
+static int sweep_blocks(size_t n4) {
   constexpr int NSB = sweep_nsb<T, LS>();
   constexpr size_t smem = (size_t)2 * VecOf<T>::NB * NSB * (LS + 1) * 16;
-  static bool configured = false;
-  if (!configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(k_s_sweep<T, LS, NSB, UPD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
   int ntiles = (int)((n4 + NSB - 1) / NSB);
   int per_sm = (int)(200 * 1024 / smem);
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 4) per_sm = 4;
   int blocks = sm_count() * per_sm;
   if (blocks > ntiles) blocks = ntiles;
-  k_s_sweep<T, LS, NSB, UPD><<<blocks, NSB * VecOf<T>::NB, smem, g_stream>>>(n4, in, out, stride, P, ntiles, upd);
+  return blocks;
+}
+
+template <typename T, int LS, bool UPD, bool EPI = false>
+static void launch_sweep(size_t n4, const T* in, T* out, size_t stride, const SweepParams<T>& P, const UpdateArgs<T>& upd,
+                         const SubDotArgs<T>& epi = SubDotArgs<T>()) {
+  constexpr int NSB = sweep_nsb<T, LS>();
+  constexpr size_t smem = (size_t)2 * VecOf<T>::NB * NSB * (LS + 1) * 16;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(k_s_sweep<T, LS, NSB, UPD, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  int ntiles = (int)((n4 + NSB - 1) / NSB);
+  int blocks = sweep_blocks<T, LS>(n4);
+  k_s_sweep<T, LS, NSB, UPD, EPI><<<blocks, NSB * VecOf<T>::NB, smem, g_stream>>>(n4, in, out, stride, P, ntiles, upd, epi);
+}
+
+// out = z - S in with optional <dotp, out>, |out|^2; returns the number of CTAs (= rows of partial) or 0 if Ls has no kernel
+template <typename T>
+static int launch_sweep_epi(int ls, size_t n4, const T* in, T* out, size_t stride, const SweepParams<T>& P, const SubDotArgs<T>& epi) {
+  UpdateArgs<T> none;
+  memset(&none, 0, sizeof(none));
+  switch (ls) {
+    case 4: launch_sweep<T, 4, false, true>(n4, in, out, stride, P, none, epi); return sweep_blocks<T, 4>(n4);
+    case 6: launch_sweep<T, 6, false, true>(n4, in, out, stride, P, none, epi); return sweep_blocks<T, 6>(n4);
+    case 8: launch_sweep<T, 8, false, true>(n4, in, out, stride, P, none, epi); return sweep_blocks<T, 8>(n4);
+    case 12: launch_sweep<T, 12, false, true>(n4, in, out, stride, P, none, epi); return sweep_blocks<T, 12>(n4);
+    case 16: launch_sweep<T, 16, false, true>(n4, in, out, stride, P, none, epi); return sweep_blocks<T, 16>(n4);
+    case 24: launch_sweep<T, 24, false, true>(n4, in, out, stride, P, none, epi); return sweep_blocks<T, 24>(n4);
+    default: return 0;
+  }
 }
 
 template <typename T, bool UPD>
@@ -212,6 +278,39 @@ bool op_cg_update_sweep(cgptb_fermion_operator* op, double a, double b, cgptb_la
   CGPTB_ASSERT(same_shape(p, r) && same_shape(p, psi) && same_shape(p, t));
   bool ok = op->prec == CGPTB_SINGLE ? cg_update_t<float>(op, a, b, p, r, psi, t) : cg_update_t<double>(op, a, b, p, r, psi, t);
   if (ok) t->cb = p->cb;
+  return ok;
+}
+
+bool sweep_supported(int ls);
+double* blas_partial_scratch(int nblocks);  // blas.cu
+void blas_finalize(int nblocks, int ncomp, const double* partial, double* host_out);
+
+// out = z - S in (S = the fused fifth-dimension operator `mode`); dot (optional, 3 doubles): re, im of <dotp, out> and |out|^2,
+// global sums inside the solver.  false if this operator / Ls has no sweep kernel.
+template <typename T>
+static bool sweep_sub_dot_t(cgptb_fermion_operator* op, int mode, const cgptb_lattice* in, const cgptb_lattice* z, cgptb_lattice* out,
+                            const cgptb_lattice* dotp, double* dot) {
+  SweepParams<T> P;
+  if (!make_sweep_params<T>(op, mode, P)) return false;
+  const int ls = op->Ls;
+  const size_t n4 = in->sites / ls;
+  SubDotArgs<T> epi;
+  epi.z = (const T*)z->data;
+  epi.dotp = dot ? (const T*)dotp->data : 0;
+  epi.partial = dot ? blas_partial_scratch(sm_count() * 4) : 0;
+  const int ctas = launch_sweep_epi<T>(ls, n4, (const T*)in->data, (T*)out->data, in->sites, P, epi);
+  if (!ctas) return false;
+  LAUNCH_CHECK();
+  if (dot) blas_finalize(ctas, 3, epi.partial, dot);
+  return true;
+}
+
+bool op_s_sweep_sub_dot(cgptb_fermion_operator* op, int mode, const cgptb_lattice* in, const cgptb_lattice* z, cgptb_lattice* out,
+                        const cgptb_lattice* dotp, double* dot) {
+  if (op->type != CGPTB_MOBIUS || op->zmobius || !sweep_supported(op->Ls)) return false;
+  CGPTB_ASSERT(same_shape(in, z) && same_shape(in, out) && (!dot || same_shape(in, dotp)) && in->data != out->data);
+  bool ok = op->prec == CGPTB_SINGLE ? sweep_sub_dot_t<float>(op, mode, in, z, out, dotp, dot) : sweep_sub_dot_t<double>(op, mode, in, z, out, dotp, dot);
+  if (ok) out->cb = in->cb;
   return ok;
 }
 

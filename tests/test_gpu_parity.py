@@ -1079,3 +1079,67 @@ def test_stencil_matrix_vector(g, fields, precision):
     assert rel(from_spinor(d0, s4), ref0) < tol and rel(from_spinor(d1, s4), ref1) < tol
     with pytest.raises(Exception):
         g.stencil.matrix_vector(Ug[0], src, [(0, 0, 0, 0)], [(0, 1, 0, -1, 1.0, []), (0, 1, 0, -1, 1.0, [])], code_parallel_block_size=3)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE.json's full size (configs[2]: Moebius 32^3 x 64, Ls = 12, single; 148 CTAs x 880 work items of the TMA sweep
+# kernel) through size-independent properties -- the oracle does this lattice only on sampled sites (bench.py's parity
+# field): adjointness <y, D x> = <D^dag y, x>, linearity, |Mpc x|^2 = <x, Mpc^dag Mpc x>, even-odd decomposition
+# Dhop = DhopEO + DhopOE, and the chunk split (CGPTB_TMA_G) leaving the result unchanged up to the order of two additions
+# ---------------------------------------------------------------------------------------------------------
+def test_full_size_properties(g, monkeypatch):
+    dims, Ls = [32, 32, 32, 64], 12
+    grid = g.grid(dims, g.single)
+    rng = g.random("full size", "vectorized_ranlux24_24_64")
+    U = g.qcd.gauge.random(grid, rng, scale=0.5)
+    m = g.qcd.fermion.mobius(U, dict(mass=0.08, M5=1.8, b=1.5, c=0.5, Ls=Ls, boundary_phases=[1.0, 1.0, 1.0, -1.0]))
+    x, y = g.vspincolor(m.F_grid), g.vspincolor(m.F_grid)
+    rng.cnormal([x, y])
+    Dx = g(m.Dhop * x)
+    Ddy = g(m.Dhop.adj() * y)
+    nx, ny, nDx = g.norm2(x), g.norm2(y), g.norm2(Dx)
+    # adjointness (reductions are double precision; the fields are single)
+    a, b = g.inner_product(y, Dx), g.inner_product(Ddy, x)
+    assert abs(a - b) / (ny * nDx) ** 0.5 < 1e-6
+    assert 0.1 < nDx / nx < 100.0
+    # linearity
+    ca, cb = 0.7 - 0.2j, -1.3 + 0.5j
+    z = g(ca * x + cb * y)
+    Dz = g(m.Dhop * z)
+    Dy = g(m.Dhop * y)
+    assert (g.norm2(g(Dz - ca * Dx - cb * Dy)) / g.norm2(Dz)) ** 0.5 < 2e-6
+    # Dhop only connects the two parities: the even-odd entries on the two halves reproduce it
+    xe, xo = g.vspincolor(m.F_grid_eo), g.vspincolor(m.F_grid_eo)
+    g.pick_checkerboard(g.even, xe, x)
+    g.pick_checkerboard(g.odd, xo, x)
+    full = g.vspincolor(m.F_grid)
+    g.set_checkerboard(full, g(m.DhopEO * xe))
+    g.set_checkerboard(full, g(m.DhopEO * xo))
+    assert g.norm2(g(full - Dx)) == 0.0
+    # one and three chunks of the fifth dimension per CTA: the same arithmetic, the two x hops summed in the other order
+    monkeypatch.setenv("CGPTB_TMA_G", "3")
+    D3 = g(m.Dhop * x)
+    monkeypatch.delenv("CGPTB_TMA_G")
+    assert (g.norm2(g(D3 - Dx)) / nDx) ** 0.5 < 1e-6
+    # Schur complement and its normal equation (the fused even-odd paths): <x, Mpc^dag Mpc x> = |Mpc x|^2
+    pc = g.qcd.fermion.preconditioner
+    Mpc = pc.eo2()(m).Mpc
+    NE = pc.eo2_ne()(m).Mpc
+    g.pick_checkerboard(g.odd, xo, x)
+    v = g(Mpc * xo)
+    w = g(NE * xo)
+    assert abs(g.inner_product(xo, w).real - g.norm2(v)) / g.norm2(v) < 1e-5
+    assert abs(g.inner_product(xo, w).imag) / g.norm2(v) < 1e-5
+
+
+def test_random_on_checkerboarded_lattice(g):
+    """the reference samples a checkerboarded lattice over its reduced coordinates (x/2, y, z, t) (lib/cgpt/lib/random/parallel.h:
+    27-128; used by tests/qcd/fermion_operators.py:649-654): same numbers as a full lattice of the reduced extents"""
+    for dims, Ls in [([8, 4, 4, 4], 0), ([8, 8, 4, 4], 4)]:
+        grid = g.grid(([Ls] if Ls else []) + dims, g.double).checkerboarded(g.redblack)
+        l = g.vspincolor(grid)
+        l.checkerboard(g.odd)
+        g.random("cb lattice").cnormal(l)
+        red = ([Ls] if Ls else []) + [dims[0] // 2] + dims[1:]
+        ref = oracle_random("cb lattice").cnormal(red, (4, 3))
+        assert rel(l[:], ref.reshape(-1, 4, 3)) < 1e-15

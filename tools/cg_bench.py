@@ -13,16 +13,12 @@ def main():
     maxiter = int(os.environ.get("CG_MAXITER", "100"))
     cgpt.init(0)
     grid = g.grid(dims, g.single)
-    U_t, src_t = bench.synthetic_fields_device(torch, dims, Ls, 99)
-    U = []
-    for mu in range(4):
-        u = g.mcolor(grid)
-        cgpt.lattice_import_device(u.obj, U_t[mu].data_ptr(), U_t[mu].numel() * 8)
-        U.append(u)
+    rng = g.random("benchmark", "vectorized_ranlux24_24_64")
+    U = g.qcd.gauge.random(grid, rng, scale=0.5)
     p = dict(bench.MOBIUS); p["Ls"] = Ls
     qm = g.qcd.fermion.mobius(U, p)
     src = g.vspincolor(qm.F_grid)
-    cgpt.lattice_import_device(src.obj, src_t.data_ptr(), src_t.numel() * 8)
+    rng.cnormal(src)
     half = g.vspincolor(qm.F_grid_eo)
     g.pick_checkerboard(g.odd, half, src)
     psi = g.lattice(half); psi[:] = 0
