@@ -5,18 +5,15 @@
 // chain of stages, e.g. T = (b + c S5)(bee - cee S5)^-1 = "Meooe5D o MooeeInv" in a single pass over the field:
 // 48 reals of traffic per site instead of 96 (+ the dense Ls x Ls product) of the unfused kernels.
 //
-// Pure HBM streaming, so it is written as a persistent kernel: CTAs loop over tiles of NSB sites, tile i+1 is
-// fetched with cp.async (global -> shared, no register staging, s fastest = fully coalesced) while tile i is swept
-// in registers and written back.
+// Pure HBM streaming, so it is written as a persistent kernel: CTAs loop over tiles of NSB sites, tile i+1 is fetched with
+// bulk copies (cp.async.bulk global -> shared, one per (32-byte component plane, site): the Ls x 32 B of a site are contiguous;
+// completion on an mbarrier, no register staging) while tile i is swept in registers and written back.  (Until round 2 the
+// tile was fetched with 16-byte cp.async: LDGSTS does not merge the two halves of a 32-byte sector, 2.4 GB came through L2 for
+// 1.2 GB of data and the kernel ran at 4.6 TB/s.)
 #include <string.h>
 #include "sweep.cuh"
 
 namespace cgptb {
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
-}
 
 // d[0..1] += conj(a) * b summed over the complex numbers of a 16-byte unit, d[2] += |b|^2, in double
 __device__ __forceinline__ void vdot_acc(float4 a, float4 b, double (&d)[3]) {
@@ -49,49 +46,94 @@ struct SubDotArgs {
   double* partial; // [ctas][3]
 };
 
+__device__ __forceinline__ uint32_t sw_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sw_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; spin++) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 24)) __trap();
+  }
+}
+
 template <typename T, int LS, int NSB, bool UPD, bool EPI = false>
 __global__ void __launch_bounds__(NSB* VecOf<T>::NB, 2) k_s_sweep(size_t n4, const T* __restrict__ in, T* __restrict__ out,
                                                                size_t stride, SweepParams<T> P, int ntiles, UpdateArgs<T> upd,
                                                                SubDotArgs<T> epi = SubDotArgs<T>()) {
   typedef typename VecOf<T>::type V;
   constexpr int NB = VecOf<T>::NB;
-  constexpr int PITCH = LS + 1;  // vectors per (block, site) row in shared memory: conflict-free column reads
-  constexpr int BUF = NB * NSB * PITCH;
+  constexpr int NPL = NB / 2;            // 32-byte component planes
+  constexpr int ROWB = LS * 32 + 16;     // bytes of one (plane, site) row in shared memory: Ls x 32 B + 16 B, so that the
+                                         // 16-byte column reads of 8 consecutive sites fall into different banks
+  constexpr int BUFB = NPL * NSB * ROWB;
   constexpr int NT = NSB * NB;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  V* sm = reinterpret_cast<V*>(smem_raw);
-  const V* gin = reinterpret_cast<const V*>(in);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* sm = smem_raw;
+  const uint32_t bar0 = sw_smem_u32(smem_raw + 2 * BUFB);
   V* gout = reinterpret_cast<V*>(out);
+  // element (16-byte unit k = 2 * plane + half, site l, slice s) of a buffer
+  auto at = [&](unsigned char* buf, int k, int l, int s) -> V& {
+    return *reinterpret_cast<V*>(buf + ((k >> 1) * NSB + l) * ROWB + s * 32 + (k & 1) * 16);
+  };
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
 
-  auto prefetch = [&](int tile, V* buf) {
+  auto prefetch = [&](int tile, int b) {
     size_t site0 = (size_t)tile * NSB;
     int nloc = (int)((n4 - site0) < (size_t)NSB ? (n4 - site0) : NSB);
+    const uint32_t bar = bar0 + 8 * b;
+    // the buffer was read and written through the generic proxy by the previous tile: order that before the bulk copies
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (threadIdx.x == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(NPL * nloc * LS * 32)) : "memory");
+    if (EPI) {
+      // z and dotp of that tile are read element-wise after the sweep: pull them into L2 now (no registers held)
 #pragma unroll
-    for (int it = 0; it < LS; it++) {
-      int idx = threadIdx.x + it * NT;
-      int half = idx & 1, q = idx >> 1;
-      int kb = q / (NSB * LS), rem = q - kb * (NSB * LS);
-      int k = 2 * kb + half;
-      int l = rem / LS, s = rem - l * LS;
-      if (l < nloc) cp_async16(buf + (k * NSB + l) * PITCH + s, gin + (((size_t)kb * stride + site0 * LS + rem) << 1) + half);
+      for (int it = 0; it < LS; it++) {
+        int idx = threadIdx.x + it * NT;
+        int q = idx >> 1;
+        int kb = q / (NSB * LS), rem = q - kb * (NSB * LS);
+        if (!(idx & 1) && rem / LS < nloc) {  // one prefetch per 32-byte sector
+          size_t o = ((size_t)kb * stride + site0 * LS + rem) << 1;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const V*>(epi.z) + o));
+          if (epi.dotp) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const V*>(epi.dotp) + o));
+        }
+      }
     }
-    asm volatile("cp.async.commit_group;");
+    for (int r = threadIdx.x; r < NPL * NSB; r += NT) {
+      const int kb = r / NSB, l = r - kb * NSB;
+      if (l < nloc) {
+        const T* src = in + ((size_t)kb * stride + (site0 + l) * LS) * (32 / sizeof(T));
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         sw_smem_u32(sm + (size_t)b * BUFB + (kb * NSB + l) * ROWB)),
+                     "l"(src), "r"((uint32_t)(LS * 32)), "r"(bar)
+                     : "memory");
+      }
+    }
   };
 
   double dsum[3] = {0.0, 0.0, 0.0};
   int tile = blockIdx.x;
-  if (tile < ntiles) prefetch(tile, sm);
+  if (tile < ntiles) prefetch(tile, 0);
   int cur = 0;
+  uint32_t phase[2] = {0, 0};
   for (; tile < ntiles; tile += gridDim.x, cur ^= 1) {
-    V* buf = sm + cur * BUF;
+    unsigned char* buf = sm + (size_t)cur * BUFB;
     int next = tile + gridDim.x;
-    if (next < ntiles) {
-      prefetch(next, sm + (cur ^ 1) * BUF);
-      asm volatile("cp.async.wait_group 1;");
-    } else {
-      asm volatile("cp.async.wait_group 0;");
-    }
-    __syncthreads();
+    if (next < ntiles) prefetch(next, cur ^ 1);
+    sw_mbar_wait(bar0 + 8 * cur, phase[cur]);
+    phase[cur] ^= 1u;
     size_t site0 = (size_t)tile * NSB;
     int nloc = (int)((n4 - site0) < (size_t)NSB ? (n4 - site0) : NSB);
     if (UPD) {
@@ -128,11 +170,11 @@ __global__ void __launch_bounds__(NSB* VecOf<T>::NB, 2) k_s_sweep(size_t n4, con
             int l = rem / LS, s = rem - l * LS;
             if (l < nloc) {
               size_t o = (((size_t)kb * stride + site0 * LS + rem) << 1) + half;
-              V pv = buf[(k * NSB + l) * PITCH + s];
+              V pv = at(buf, k, l, s);
               __stcs(gpsi + o, vfma(upd.a, pv, sv[c]));
               V pn = vfma(upd.b, pv, rv[c]);
               __stcs(gp + o, pn);
-              buf[(k * NSB + l) * PITCH + s] = pn;
+              at(buf, k, l, s) = pn;
             }
           }
         }
@@ -141,24 +183,59 @@ __global__ void __launch_bounds__(NSB* VecOf<T>::NB, 2) k_s_sweep(size_t n4, con
     }
     {
       int l = threadIdx.x % NSB, k = threadIdx.x / NSB;
-      if (l < nloc) sweep_row<T, LS>(P, k, buf + (k * NSB + l) * PITCH);
+      if (l < nloc) sweep_row<T, LS, 2>(P, k, &at(buf, k, l, 0));
     }
     __syncthreads();
+    if (EPI) {
+      // out = z - (swept), partial sums of <dotp, out> and |out|^2: the loads of z and dotp go out CH at a time
+      constexpr int CH = 4;
+      const V* gz = reinterpret_cast<const V*>(epi.z);
+      const V* gd = reinterpret_cast<const V*>(epi.dotp);
 #pragma unroll
-    for (int it = 0; it < LS; it++) {
-      int idx = threadIdx.x + it * NT;
-      int half = idx & 1, q = idx >> 1;
-      int kb = q / (NSB * LS), rem = q - kb * (NSB * LS);
-      int k = 2 * kb + half;
-      int l = rem / LS, s = rem - l * LS;
-      if (l < nloc) {
-        const size_t o = (((size_t)kb * stride + site0 * LS + rem) << 1) + half;
-        V r = buf[(k * NSB + l) * PITCH + s];
-        if (EPI) {
-          r = vfma((T)-1, r, __ldcs(reinterpret_cast<const V*>(epi.z) + o));
-          if (epi.dotp) vdot_acc(__ldcs(reinterpret_cast<const V*>(epi.dotp) + o), r, dsum);
+      for (int it0 = 0; it0 < LS; it0 += CH) {
+        V zv[CH], dv[CH];
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+          int it = it0 + c;
+          if (it < LS) {
+            int idx = threadIdx.x + it * NT;
+            int half = idx & 1, q = idx >> 1;
+            int kb = q / (NSB * LS), rem = q - kb * (NSB * LS);
+            int l = rem / LS;
+            if (l < nloc) {
+              size_t o = (((size_t)kb * stride + site0 * LS + rem) << 1) + half;
+              zv[c] = __ldcs(gz + o);
+              if (gd) dv[c] = __ldcs(gd + o);
+            }
+          }
         }
-        __stcs(gout + o, r);
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+          int it = it0 + c;
+          if (it < LS) {
+            int idx = threadIdx.x + it * NT;
+            int half = idx & 1, q = idx >> 1;
+            int kb = q / (NSB * LS), rem = q - kb * (NSB * LS);
+            int k = 2 * kb + half;
+            int l = rem / LS, s = rem - l * LS;
+            if (l < nloc) {
+              size_t o = (((size_t)kb * stride + site0 * LS + rem) << 1) + half;
+              V r = vfma((T)-1, at(buf, k, l, s), zv[c]);
+              if (gd) vdot_acc(dv[c], r, dsum);
+              __stcs(gout + o, r);
+            }
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < LS; it++) {
+        int idx = threadIdx.x + it * NT;
+        int half = idx & 1, q = idx >> 1;
+        int kb = q / (NSB * LS), rem = q - kb * (NSB * LS);
+        int k = 2 * kb + half;
+        int l = rem / LS, s = rem - l * LS;
+        if (l < nloc) __stcs(gout + (((size_t)kb * stride + site0 * LS + rem) << 1) + half, at(buf, k, l, s));
       }
     }
     __syncthreads();  // buf is refilled by the prefetch of the next iteration
@@ -182,10 +259,16 @@ constexpr int sweep_nsb() {
   return n;
 }
 
+// two tile buffers of (NB / 2 planes) x NSB rows of Ls x 32 B + 16 B, two mbarriers, alignment slack
+template <typename T, int LS>
+constexpr size_t sweep_smem() {
+  return (size_t)2 * (VecOf<T>::NB / 2) * sweep_nsb<T, LS>() * (LS * 32 + 16) + 128;
+}
+
 template <typename T, int LS>
 static int sweep_blocks(size_t n4) {
   constexpr int NSB = sweep_nsb<T, LS>();
-  constexpr size_t smem = (size_t)2 * VecOf<T>::NB * NSB * (LS + 1) * 16;
+  constexpr size_t smem = sweep_smem<T, LS>();
   int ntiles = (int)((n4 + NSB - 1) / NSB);
   int per_sm = (int)(200 * 1024 / smem);
   if (per_sm < 1) per_sm = 1;
@@ -199,7 +282,7 @@ template <typename T, int LS, bool UPD, bool EPI = false>
 static void launch_sweep(size_t n4, const T* in, T* out, size_t stride, const SweepParams<T>& P, const UpdateArgs<T>& upd,
                          const SubDotArgs<T>& epi = SubDotArgs<T>()) {
   constexpr int NSB = sweep_nsb<T, LS>();
-  constexpr size_t smem = (size_t)2 * VecOf<T>::NB * NSB * (LS + 1) * 16;
+  constexpr size_t smem = sweep_smem<T, LS>();
   static bool configured = false;
   if (!configured) {
     CUDA_CHECK(cudaFuncSetAttribute(k_s_sweep<T, LS, NSB, UPD, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

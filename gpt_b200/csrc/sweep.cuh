@@ -95,16 +95,17 @@ __device__ __forceinline__ void run_stage(const SweepStage<T>& st, int chi, type
 }
 
 // the sweep of one (component block k, site l) row held in shared memory: row[s], s = 0..LS-1
-template <typename T, int LS>
+// (STRIDE: distance of consecutive s in units of the 16-byte vector type)
+template <typename T, int LS, int STRIDE = 1>
 __device__ __forceinline__ void sweep_row(const SweepParams<T>& P, int k, typename VecOf<T>::type* row) {
   typename VecOf<T>::type x[LS];
 #pragma unroll
-  for (int s = 0; s < LS; s++) x[s] = row[s];
+  for (int s = 0; s < LS; s++) x[s] = row[s * STRIDE];
   int chi = k < VecOf<T>::NBU ? 0 : 1;
   run_stage<T, LS>(P.st[0], chi, x);
   if (P.nstages > 1) run_stage<T, LS>(P.st[1], chi, x);
 #pragma unroll
-  for (int s = 0; s < LS; s++) row[s] = x[s];
+  for (int s = 0; s < LS; s++) row[s * STRIDE] = x[s];
 }
 
 // stage description for B = d + f S5 (dag: S5^dag), solve or apply

@@ -20,7 +20,7 @@ the reference's own Python statement of the same maths and its golden fingerprin
   * M5D / MooeeInv structure        lib/cgpt/lib/foundation/mobius_with_vector_field.h:36-96,176-302,500-513
   * opcode table                    lib/cgpt/lib/operators/register.h:2-20
 
-Parity pin: tests/test_oracle_fingerprints.py reproduces the golden numbers of
+Parity pin: tests/test_oracle_golden.py (this repo) reproduces the golden numbers of
 /root/reference/tests/qcd/fermion_operators.py:371-459 and tests/random/simple.py:18-27.
 
 Layout ("oracle layout"): a field on a grid with dims [L0,L1,L2,L3] (x,y,z,t) is a numpy array of shape
