@@ -105,6 +105,7 @@ struct cgptb_lattice {
   size_t sites;   // stored sites (sites4 * max(Ls,1))
   void* data;
   bool owns;
+  void* alloc = 0;  // what cudaMalloc returned (data = alloc + skew, see create_lattice)
 
   int ls() const { return Ls > 0 ? Ls : 1; }
   size_t real_size() const { return prec == CGPTB_DOUBLE ? 8 : 4; }

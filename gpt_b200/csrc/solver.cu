@@ -177,7 +177,27 @@ int cgptb_cg_eo2_ne(cgptb_fermion_operator* op, cgptb_lattice* psi, const cgptb_
     double a = c / d;
     if (cgptb_lattice_axpy_norm2(r, -a, 0.0, mmp, r, &cp)) CGPTB_ERR("%s", cgptb_last_error());
     double b = cp / c;
-    if (fuse_update && op_cg_update_sweep(op, a, b, p, r, psi, tp)) {
+    static int cg_timing = getenv("CGPTB_CG_TIMING") ? 1 : 0;  // measurement aid: device time of the fused update kernel
+    static cudaEvent_t tev[2];
+    static double tacc = 0;
+    static int tn = 0;
+    if (cg_timing) {
+      if (!tn && tacc == 0) {
+        cudaEventCreate(&tev[0]);
+        cudaEventCreate(&tev[1]);
+      }
+      cudaEventRecord(tev[0], g_stream);
+    }
+    const bool fused_upd = fuse_update && op_cg_update_sweep(op, a, b, p, r, psi, tp);
+    if (cg_timing) {
+      cudaEventRecord(tev[1], g_stream);
+      cudaEventSynchronize(tev[1]);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, tev[0], tev[1]);
+      tacc += ms;
+      if (++tn % 50 == 0) fprintf(stderr, "[cg timing] update step: %.3f ms (fused %d, %d calls)\n", tacc / tn, (int)fused_upd, tn);
+    }
+    if (fused_upd) {
       have_tp = true;  // psi += a p ; p = b p + r ; tp = T p in one pass
     } else {
       double ca[2] = {a, 0.0};

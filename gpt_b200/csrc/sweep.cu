@@ -10,6 +10,7 @@
 // completion on an mbarrier, no register staging) while tile i is swept in registers and written back.  (Until round 2 the
 // tile was fetched with 16-byte cp.async: LDGSTS does not merge the two halves of a 32-byte sector, 2.4 GB came through L2 for
 // 1.2 GB of data and the kernel ran at 4.6 TB/s.)
+#include <stdlib.h>
 #include <string.h>
 #include "sweep.cuh"
 
@@ -338,6 +339,8 @@ static bool sweep_t(cgptb_fermion_operator* op, int mode, const cgptb_lattice* i
   return true;
 }
 
+__global__ void k_nop() {}
+
 // psi += a p ; p = b p + r ; t = T p   in one pass (CG update + first factor of the next Mpc)
 template <typename T>
 static bool cg_update_t(cgptb_fermion_operator* op, double a, double b, cgptb_lattice* p, const cgptb_lattice* r, cgptb_lattice* psi,
@@ -352,6 +355,9 @@ static bool cg_update_t(cgptb_fermion_operator* op, double a, double b, cgptb_la
   upd.p = (T*)p->data;
   if (!launch_sweep_ls<T, true>(op->Ls, p->sites / op->Ls, (const T*)p->data, (T*)t->data, p->sites, P, upd)) return false;
   LAUNCH_CHECK();
+  static int nop = getenv("CGPTB_UPD_NOP") ? atoi(getenv("CGPTB_UPD_NOP")) : 0;
+  if (nop == 1) k_nop<<<1, 32, 0, g_stream>>>();
+  if (nop == 2) k_nop<<<sm_count() * 2, 1024, 0, g_stream>>>();
   return true;
 }
 

@@ -1,7 +1,7 @@
 #!/bin/bash
 # kernel-by-kernel times of one CG iteration on the unfused (TMA stencil + sweep kernels) path, and a full capture of the sweep kernel
 cd "$(dirname "$0")/.."
-CG_MAXITER=6 CGPTB_NO_EPILOGUE=1 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k "regex:^k_" -c 400 --csv --log-file gpurun_out/${TAG}_cg_launches.csv python tools/cg_bench.py > /dev/null 2>&1
+env CG_MAXITER=6 ${CGENV:-CGPTB_NO_EPILOGUE=1} ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k "regex:^k_" -c 400 --csv --log-file gpurun_out/${TAG}_cg_launches.csv python tools/cg_bench.py > /dev/null 2>&1
 python - <<PY
 import csv
 rows = [r for r in csv.reader(open("gpurun_out/${TAG}_cg_launches.csv")) if len(r) > 5]
