@@ -13,6 +13,10 @@
 namespace cgptb {
 
 bool g_reduce_global = false;  // solver.cu: sum reduction results over all ranks before they reach the host
+// solver.cu, device-resident CG: reduction results stay on the device (no copy, no synchronisation); the pointer to the last
+// result is left in g_reduce_dev_ptr
+bool g_reduce_to_device = false;
+double* g_reduce_dev_ptr = 0;
 
 static const int BT = 256;
 static const int UNROLL = 4;
@@ -74,8 +78,12 @@ template <typename T, bool NORM>
 // no pointer carries __restrict__ (the loads must not be moved to the read-only path)
 __global__ void __launch_bounds__(BT) k_axpy(size_t nvec, T ar, T ai, const typename V<T>::vec* x,
                                              const typename V<T>::vec* y, typename V<T>::vec* r,
-                                             double* __restrict__ partial) {
+                                             double* __restrict__ partial, const double* scal_dev = 0, double scal_mult = 0.0) {
   typedef typename V<T>::vec vec;
+  if (scal_dev) {  // real scalar computed on the device (CG: a = c / d)
+    ar = (T)(scal_mult * *scal_dev);
+    ai = (T)0;
+  }
   double s = 0.0;
   size_t stride = (size_t)gridDim.x * BT;
   for (size_t i = (size_t)blockIdx.x * BT + threadIdx.x; i < nvec; i += stride * UNROLL) {
@@ -205,6 +213,33 @@ static void axpy_t(cgptb_lattice* r, double are, double aim, const cgptb_lattice
   *norm2 = h[0];
 }
 
+// r = (mult * *scal_dev) x + y and |r|^2, everything on the device: returns where the (globally summed) |r|^2 is
+double* blas_axpy_norm2_dev(cgptb_lattice* r, const double* scal_dev, double mult, const cgptb_lattice* x, const cgptb_lattice* y) {
+  CGPTB_ASSERT(same_shape(r, x) && same_shape(r, y));
+  check_vec(r);
+  r->cb = x->cb;
+  double* part = reduce_scratch((size_t)sm_count() * 8 * 3 + 8);
+  double* out = part + (size_t)sm_count() * 8 * 3;
+  if (r->prec == CGPTB_SINGLE) {
+    typedef V<float>::vec vec;
+    size_t nvec = nvec_of<float>(x);
+    unsigned g = grid_for(nvec);
+    k_axpy<float, true><<<g, BT, 0, g_stream>>>(nvec, 0.f, 0.f, (const vec*)x->data, (const vec*)y->data, (vec*)r->data, part, scal_dev, mult);
+    LAUNCH_CHECK();
+    k_final<<<1, BT, 0, g_stream>>>((int)g, 1, part, out);
+  } else {
+    typedef V<double>::vec vec;
+    size_t nvec = nvec_of<double>(x);
+    unsigned g = grid_for(nvec);
+    k_axpy<double, true><<<g, BT, 0, g_stream>>>(nvec, 0.0, 0.0, (const vec*)x->data, (const vec*)y->data, (vec*)r->data, part, scal_dev, mult);
+    LAUNCH_CHECK();
+    k_final<<<1, BT, 0, g_stream>>>((int)g, 1, part, out);
+  }
+  LAUNCH_CHECK();
+  if (g_reduce_global) comm_allreduce_device(out, 1, g_stream);
+  return out;
+}
+
 void blas_axpy(cgptb_lattice* r, double are, double aim, const cgptb_lattice* x, const cgptb_lattice* y) {
   CGPTB_ASSERT(same_shape(r, x) && same_shape(r, y));
   check_vec(r);
@@ -262,6 +297,10 @@ void blas_finalize(int nblocks, int ncomp, const double* partial, double* host_o
   k_final<<<1, BT, 0, g_stream>>>(nblocks, ncomp, partial, out);
   LAUNCH_CHECK();
   if (g_reduce_global) comm_allreduce_device(out, ncomp, g_stream);
+  if (g_reduce_to_device) {
+    g_reduce_dev_ptr = out;
+    return;
+  }
   double* h = reduce_host(8);
   CUDA_CHECK(cudaMemcpyAsync(h, out, ncomp * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
   CUDA_CHECK(cudaStreamSynchronize(g_stream));

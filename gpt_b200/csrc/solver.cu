@@ -21,7 +21,37 @@ void dhop_half_f32_fused(cgptb_fermion_operator* op, bool dag, const float* pin,
                          double* partial);
 bool sweep_supported(int ls);  // sweep.cu
 bool op_cg_update_sweep(cgptb_fermion_operator* op, double a, double b, cgptb_lattice* p, const cgptb_lattice* r, cgptb_lattice* psi,
-                        cgptb_lattice* t);
+                        cgptb_lattice* t, const double* ab_dev = 0);
+double* blas_axpy_norm2_dev(cgptb_lattice* r, const double* scal_dev, double mult, const cgptb_lattice* x, const cgptb_lattice* y);  // blas.cu
+extern bool g_reduce_to_device;
+extern double* g_reduce_dev_ptr;
+
+// Scalars of the CG on the device (cg.py:70-112): the loop runs without a host round trip per iteration; the host reads `done`
+// and `iter` every few iterations.  After convergence a = 0, so the iterations that were already queued leave psi and r alone.
+struct CgState {
+  double a, b;  // (a, b) contiguous: the fused update kernel reads them as ab_dev[0..1]
+  double c, rsq;
+  int done, iter;
+};
+// mode 0: red[0] = <p, A p>  ->  a = c / d
+// mode 1: red[0] = |r|^2     ->  b = cp / c ; history[iter++] = |cp| ; done if |cp| <= rsq ; c = cp
+__global__ void k_cg_step(CgState* S, double* hist, int mode, const double* red) {
+  if (mode == 0) {
+    S->a = S->done ? 0.0 : S->c / red[0];
+  } else {
+    const double cp = red[0];
+    if (S->done) {
+      S->b = 1.0;
+    } else {
+      S->b = cp / S->c;
+      const double res = fabs(cp);
+      hist[S->iter] = res;
+      S->iter++;
+      if (res <= S->rsq) S->done = 1;
+      S->c = cp;
+    }
+  }
+}
 bool op_s_sweep_sub_dot(cgptb_fermion_operator* op, int mode, const cgptb_lattice* in, const cgptb_lattice* z, cgptb_lattice* out,
                         const cgptb_lattice* dotp, double* dot);
 void blas_finalize(int nblocks, int ncomp, const double* partial, double* host_out);  // blas.cu
@@ -169,6 +199,63 @@ int cgptb_cg_eo2_ne(cgptb_fermion_operator* op, cgptb_lattice* psi, const cgptb_
     return 0;
   }
   double rsq = eps * eps * ssq;
+  // device-resident scalars (Moebius with the fused update + sweep kernels; CGPTB_CG_HOST=1: the host loop below)
+  static int cg_host = getenv("CGPTB_CG_HOST") ? 1 : 0;
+  static int cg_chunk = getenv("CGPTB_CG_CHUNK") ? atoi(getenv("CGPTB_CG_CHUNK")) : 6;
+  if (fuse_update && !cg_host && maxiter > 0) {
+    CgState* S = 0;
+    double* hist = 0;
+    CUDA_CHECK(cudaMalloc(&S, sizeof(CgState)));
+    CUDA_CHECK(cudaMalloc(&hist, sizeof(double) * (size_t)maxiter));
+    struct Free {
+      void *a, *b;
+      ~Free() {
+        cudaFree(a);
+        cudaFree(b);
+      }
+    } fr{S, hist};
+    CgState h;
+    h.a = h.b = 0.0;
+    h.c = cp;
+    h.rsq = rsq;
+    h.done = 0;
+    h.iter = 0;
+    CUDA_CHECK(cudaMemcpyAsync(S, &h, sizeof(h), cudaMemcpyHostToDevice, g_stream));
+    CUDA_CHECK(cudaStreamSynchronize(g_stream));  // h is a stack object
+    int k = 0;
+    while (k < maxiter) {
+      const int chunk = cg_chunk < 1 ? 1 : (maxiter - k < cg_chunk ? maxiter - k : cg_chunk);
+      for (int j = 0; j < chunk; j++) {
+        double dummy[3];
+        g_reduce_to_device = true;
+        g_reduce_dev_ptr = 0;
+        try {
+          mat(mmp, p, dummy);  // <p, mmp> stays on the device
+        } catch (...) {
+          g_reduce_to_device = false;
+          throw;
+        }
+        g_reduce_to_device = false;
+        if (!g_reduce_dev_ptr) CGPTB_ERR("device CG: the matrix application left no reduction on the device");
+        k_cg_step<<<1, 1, 0, g_stream>>>(S, hist, 0, g_reduce_dev_ptr);
+        LAUNCH_CHECK();
+        double* cp_dev = blas_axpy_norm2_dev(r, &S->a, -1.0, mmp, r);
+        k_cg_step<<<1, 1, 0, g_stream>>>(S, hist, 1, cp_dev);
+        LAUNCH_CHECK();
+        if (!op_cg_update_sweep(op, 0.0, 0.0, p, r, psi, tp, &S->a)) CGPTB_ERR("device CG: fused update kernel missing");
+        have_tp = true;
+      }
+      k += chunk;
+      CUDA_CHECK(cudaMemcpyAsync(&h, S, sizeof(h), cudaMemcpyDeviceToHost, g_stream));
+      CUDA_CHECK(cudaStreamSynchronize(g_stream));
+      if (h.done) break;
+    }
+    *iterations = h.iter;
+    *converged = h.done;
+    if (history && h.iter > 0) CUDA_CHECK(cudaMemcpy(history, hist, sizeof(double) * (size_t)h.iter, cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaStreamSynchronize(g_stream));
+    return 0;
+  }
   for (int k = 0; k < maxiter; k++) {
     double c = cp;
     double ip[3];

@@ -33,6 +33,7 @@ __device__ __forceinline__ void vdot_acc(double2 a, double2 b, double (&d)[3]) {
 template <typename T>
 struct UpdateArgs {
   T a, b;
+  const double* ab_dev;  // if set: a = ab_dev[0], b = ab_dev[1] (computed on the device by the CG)
   const T* r;
   T* psi;
   T* p;
@@ -124,6 +125,10 @@ __global__ void __launch_bounds__(NSB* VecOf<T>::NB, 2) k_s_sweep(size_t n4, con
     }
   };
 
+  if (UPD && upd.ab_dev) {
+    upd.a = (T)upd.ab_dev[0];
+    upd.b = (T)upd.ab_dev[1];
+  }
   double dsum[3] = {0.0, 0.0, 0.0};
   int tile = blockIdx.x;
   if (tile < ntiles) prefetch(tile, 0);
@@ -344,12 +349,13 @@ __global__ void k_nop() {}
 // psi += a p ; p = b p + r ; t = T p   in one pass (CG update + first factor of the next Mpc)
 template <typename T>
 static bool cg_update_t(cgptb_fermion_operator* op, double a, double b, cgptb_lattice* p, const cgptb_lattice* r, cgptb_lattice* psi,
-                        cgptb_lattice* t) {
+                        cgptb_lattice* t, const double* ab_dev) {
   SweepParams<T> P;
   if (!make_sweep_params<T>(op, SWEEP_T, P)) return false;
   UpdateArgs<T> upd;
   upd.a = (T)a;
   upd.b = (T)b;
+  upd.ab_dev = ab_dev;
   upd.r = (const T*)r->data;
   upd.psi = (T*)psi->data;
   upd.p = (T*)p->data;
@@ -362,10 +368,10 @@ static bool cg_update_t(cgptb_fermion_operator* op, double a, double b, cgptb_la
 }
 
 bool op_cg_update_sweep(cgptb_fermion_operator* op, double a, double b, cgptb_lattice* p, const cgptb_lattice* r, cgptb_lattice* psi,
-                        cgptb_lattice* t) {
+                        cgptb_lattice* t, const double* ab_dev) {
   if (op->type != CGPTB_MOBIUS || !(op->Ls == 4 || op->Ls == 6 || op->Ls == 8 || op->Ls == 12 || op->Ls == 16 || op->Ls == 24)) return false;
   CGPTB_ASSERT(same_shape(p, r) && same_shape(p, psi) && same_shape(p, t));
-  bool ok = op->prec == CGPTB_SINGLE ? cg_update_t<float>(op, a, b, p, r, psi, t) : cg_update_t<double>(op, a, b, p, r, psi, t);
+  bool ok = op->prec == CGPTB_SINGLE ? cg_update_t<float>(op, a, b, p, r, psi, t, ab_dev) : cg_update_t<double>(op, a, b, p, r, psi, t, ab_dev);
   if (ok) t->cb = p->cb;
   return ok;
 }
