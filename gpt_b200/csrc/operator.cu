@@ -1494,6 +1494,8 @@ int cgptb_delete_fermion_operator(cgptb_fermion_operator* op) {
       if (op->tmp_full[i]) cgptb_delete_lattice(op->tmp_full[i]);
       if (op->tmp_half[i]) cgptb_delete_lattice(op->tmp_half[i]);
     }
+    for (int i = 0; i < 5; i++)
+      if (op->cg_half[i]) cgptb_delete_lattice(op->cg_half[i]);
     delete op;
   }
   CGPTB_API_END

@@ -35,6 +35,7 @@ struct cgptb_fermion_operator {
   void* z_tab = 0;              // zMoebius: dense complex blocks [kind 5][dag 2][P+, P-][Ls][Ls][re, im]
   cgptb_lattice* tmp_full[4] = {0, 0, 0, 0};
   cgptb_lattice* tmp_half[4] = {0, 0, 0, 0};
+  cgptb_lattice* cg_half[5] = {0, 0, 0, 0, 0};  // work fields of cgptb_cg_eo2_ne (p, mmp, r, v, T p), kept between solves
   // multi-GPU decomposition (halo.cu); g.comm_mask marks the split directions
   int goff[4] = {0, 0, 0, 0};   // global coordinate of the local origin
   int gL[4] = {0, 0, 0, 0};     // global extents

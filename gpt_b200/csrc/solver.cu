@@ -159,20 +159,18 @@ int cgptb_cg_eo2_ne(cgptb_fermion_operator* op, cgptb_lattice* psi, const cgptb_
   psi->cb = src->cb;
   *iterations = 0;
   *converged = 0;
-  cgptb_lattice *p = 0, *mmp = 0, *r = 0, *v = 0, *tp = 0;
-  cgptb_lattice** all[5] = {&p, &mmp, &r, &v, &tp};
-  struct Guard {
-    cgptb_lattice*** a;
-    ~Guard() {
-      for (int i = 0; i < 5; i++)
-        if (*a[i]) cgptb_delete_lattice(*a[i]);
-    }
-  } guard{all};
+  // work fields: kept in the operator between solves (allocating and freeing five fields of the lattice's size per solve costs
+  // tens to hundreds of milliseconds in cudaFree alone and showed as a "slow first solve" / bimodal time per iteration)
   static int no_upd = getenv("CGPTB_NO_FUSED_UPDATE") ? 1 : 0;
   static int no_sweep_cg = getenv("CGPTB_NO_SWEEP") ? 1 : 0;
   bool fuse_update = !no_upd && !no_sweep_cg && op->type == CGPTB_MOBIUS && !op->zmobius && sweep_supported(op->Ls);
-  for (int i = 0; i < (fuse_update ? 5 : 4); i++)
-    if (cgptb_create_lattice(all[i], op->dims4, op->Ls, op->prec, CGPTB_OT_VSPINCOLOR, src->cb)) CGPTB_ERR("%s", cgptb_last_error());
+  cgptb_lattice* w[5];
+  for (int i = 0; i < (fuse_update ? 5 : 4); i++) {
+    if (!op->cg_half[i] && cgptb_create_lattice(&op->cg_half[i], op->dims4, op->Ls, op->prec, CGPTB_OT_VSPINCOLOR, src->cb)) CGPTB_ERR("%s", cgptb_last_error());
+    op->cg_half[i]->cb = src->cb;
+    w[i] = op->cg_half[i];
+  }
+  cgptb_lattice *p = w[0], *mmp = w[1], *r = w[2], *v = w[3], *tp = fuse_update ? w[4] : 0;
 
   struct GlobalSums {  // reductions inside the solver are global sums (cg.py gets them via grid.globalsum)
     GlobalSums() { g_reduce_global = true; }

@@ -102,3 +102,17 @@ def test_p2p_halo_protocol_simulation(world):
     for t in threads:
         t.join(timeout=60)
     assert not errors, errors[:3]
+
+
+def test_stencil_program_lines():
+    """g.local_stencil: tuple and dictionary forms of a code line are the same program; malformed lines are refused before
+    anything reaches the library (no GPU needed)"""
+    from gpt_b200.local_stencil import _program_line
+
+    t = _program_line((0, 1, 2, -1, 0.5 - 1j, [(3, 0, 1), [1, 2, 0]]))
+    d = _program_line({"target": 0, "source": 1, "source_point": 2, "accumulate": -1, "weight": 0.5 - 1j, "factor": [(3, 0, 1), (1, 2, 0)]})
+    assert t == d and t["factor"] == [(3, 0, 1), (1, 2, 0)]
+    with pytest.raises(ValueError):
+        _program_line({"target": 0, "source": 1})
+    with pytest.raises(ValueError):
+        _program_line((0, 1, 2, -1, 1.0))
