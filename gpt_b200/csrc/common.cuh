@@ -106,6 +106,7 @@ struct cgptb_lattice {
   void* data;
   bool owns;
   void* alloc = 0;  // what cudaMalloc returned (data = alloc + skew, see create_lattice)
+  size_t alloc_bytes = 0;
 
   int ls() const { return Ls > 0 ? Ls : 1; }
   size_t real_size() const { return prec == CGPTB_DOUBLE ? 8 : 4; }

@@ -1,8 +1,43 @@
 // Runtime + lattice storage seam of libcgpt_b200 (replaces lib/cgpt/lib/lattice.cc:42-210,
 // lib/cgpt/lib/transform.cc:41-54,128-141 and lattice/implementation.h:246-281 for the hot path's objects).
+#include <map>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace cgptb {
+
+// Device memory of deleted lattices is kept for the next lattice of the same size instead of going back to the driver: the host
+// layer creates and drops temporaries all the time (every g(expr), every outer iteration of a defect-correcting solve), and
+// cudaFree of a GB-sized block costs tens to hundreds of milliseconds and synchronises the device (the reference relies on Grid's
+// memory manager cache for the same reason).  Reuse is stream-ordered like everything else in the library.  CGPTB_CACHE_GB
+// bounds what is kept (default 24; 0 switches the cache off).
+static std::multimap<size_t, void*> g_lat_cache;
+static size_t g_lat_cached = 0;
+static size_t lattice_cache_limit() {
+  static double gb = getenv("CGPTB_CACHE_GB") ? atof(getenv("CGPTB_CACHE_GB")) : 24.0;
+  return (size_t)(gb * 1e9);
+}
+static void* lattice_cache_get(size_t bytes) {
+  auto it = g_lat_cache.find(bytes);
+  if (it == g_lat_cache.end()) return 0;
+  void* p = it->second;
+  g_lat_cache.erase(it);
+  g_lat_cached -= bytes;
+  return p;
+}
+static void lattice_cache_flush() {
+  for (auto& kv : g_lat_cache) cudaFree(kv.second);
+  g_lat_cache.clear();
+  g_lat_cached = 0;
+}
+static void lattice_cache_put(void* p, size_t bytes) {
+  if (g_lat_cached + bytes <= lattice_cache_limit()) {
+    g_lat_cache.emplace(bytes, p);
+    g_lat_cached += bytes;
+  } else {
+    CUDA_CHECK(cudaFree(p));
+  }
+}
 
 thread_local std::string g_error;
 cudaStream_t g_stream = 0;
@@ -148,7 +183,14 @@ static void new_lattice(cgptb_lattice** out, const int dims4[4], int Ls, int pre
     static size_t skew_unit = getenv("CGPTB_LATTICE_SKEW") ? (size_t)atol(getenv("CGPTB_LATTICE_SKEW")) / 256 * 256 : 0;
     static unsigned counter = 0;
     const size_t skew = skew_unit * (counter++ % 16);
-    cudaError_t e = cudaMalloc(&l->alloc, l->bytes() + skew_unit * 16);
+    l->alloc_bytes = l->bytes() + skew_unit * 16;
+    l->alloc = lattice_cache_get(l->alloc_bytes);
+    cudaError_t e = l->alloc ? cudaSuccess : cudaMalloc(&l->alloc, l->alloc_bytes);
+    if (e != cudaSuccess) {  // give the cached blocks back and try once more
+      cudaGetLastError();
+      lattice_cache_flush();
+      e = cudaMalloc(&l->alloc, l->alloc_bytes);
+    }
     if (e != cudaSuccess) {
       size_t b = l->bytes();
       delete l;
@@ -277,7 +319,7 @@ int cgptb_create_lattice_view(cgptb_lattice** out, const int dims4[4], int Ls, i
 int cgptb_delete_lattice(cgptb_lattice* l) {
   CGPTB_API_BEGIN
   if (l) {
-    if (l->owns && l->alloc) CUDA_CHECK(cudaFree(l->alloc));
+    if (l->owns && l->alloc) lattice_cache_put(l->alloc, l->alloc_bytes);
     delete l;
   }
   CGPTB_API_END
