@@ -1143,3 +1143,22 @@ def test_random_on_checkerboarded_lattice(g):
         red = ([Ls] if Ls else []) + [dims[0] // 2] + dims[1:]
         ref = oracle_random("cb lattice").cnormal(red, (4, 3))
         assert rel(l[:], ref.reshape(-1, 4, 3)) < 1e-15
+
+
+def test_lattice_memory_is_reused(g):
+    """deleted lattices hand their device memory to the next lattice of the same size (lattice.cu: no cudaFree / cudaMalloc per
+    temporary of the host layer); a lattice that reuses memory is a normal lattice: zero it, fill it, read it back"""
+    from gpt_b200 import capi
+
+    grid = g.grid([8, 8, 8, 8], g.double)
+    first = [g.vspincolor(grid) for _ in range(40)]  # more than any earlier test can have left in the cache for this size
+    ptrs = sorted(capi.lattice_device_ptr(l.obj) for l in first)
+    assert len(set(ptrs)) == 40
+    del first
+    second = [g.vspincolor(grid) for _ in range(40)]
+    assert sorted(capi.lattice_device_ptr(l.obj) for l in second) == ptrs
+    b, c = second[0], second[1]
+    b[:] = 0
+    assert g.norm2(b) == 0.0
+    g.random("reuse").cnormal([b, c])
+    assert g.norm2(b) > 0 and abs(g.inner_product(b, c)) < g.norm2(b)

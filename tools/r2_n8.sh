@@ -18,7 +18,7 @@ except Exception as e:
 PY
 }
 run bench.py --gpus $N --steps 300 --warmup 10 --no-e2e --no-cpu --no-kernels --no-solve --cg-iterations 50 > gpurun_out/${TAG}_t.json 2> gpurun_out/${TAG}_t.err; show gpurun_out/${TAG}_t.json
-run bench.py --gpus $N --mpi 1.1.2.$((N/2)) --steps 300 --warmup 10 --no-e2e --no-cpu --no-kernels --no-solve --cg-iterations 50 > gpurun_out/${TAG}_tz.json 2> gpurun_out/${TAG}_tz.err; show gpurun_out/${TAG}_tz.json
+[ -n "$SKIP_TZ" ] || run bench.py --gpus $N --mpi 1.1.2.$((N/2)) --steps 300 --warmup 10 --no-e2e --no-cpu --no-kernels --no-solve --cg-iterations 50 > gpurun_out/${TAG}_tz.json 2> gpurun_out/${TAG}_tz.err; [ -n "$SKIP_TZ" ] || show gpurun_out/${TAG}_tz.json
 run bench.py --gpus $N --config clover_solve --mpi 1.1.2.$((N/2)) ${CLOVER_GRID:+--grid $CLOVER_GRID} > gpurun_out/${TAG}_c3.json 2> gpurun_out/${TAG}_c3.err; show gpurun_out/${TAG}_c3.json
 run bench.py --gpus $N --config mobius_prop ${MOBIUS_GRID:+--grid $MOBIUS_GRID} > gpurun_out/${TAG}_c4.json 2> gpurun_out/${TAG}_c4.err; show gpurun_out/${TAG}_c4.json
 grep -h -i "error\|Traceback" gpurun_out/${TAG}_*.err | head -5
