@@ -144,6 +144,30 @@ def gell_mann_half():
     return lam / 2
 
 
+def pad_with_neighbour_faces(flat, dims, ncomp, mpi, rank, gather):
+    """A rank's block of a field (GPT order: x fastest, then y, z, t; ncomp complex numbers per site) -> [T + 2, Z + 2, Y X ncomp],
+    the block padded by one slice in t and in z with the facing slices of its neighbours in the processor grid mpi = 1.1.Z.T
+    (rank = cz + Z * ct; periodic: a direction that is not split wraps onto the block itself).  gather(face) returns the
+    list of that face from every rank, in rank order.  Corners stay zero: a one-hop stencil does not read them."""
+    X, Y, Z, T = dims
+    pz, pt = mpi[2], mpi[3]
+    cz, ct = rank % pz, rank // pz
+    row = Y * X * ncomp
+    P = np.zeros((T + 2, Z + 2, row), dtype=flat.dtype)
+    P[1:-1, 1:-1] = flat.reshape(T, Z, row)
+    every = {k: gather(np.ascontiguousarray(v)) for k, v in
+             (("t_lo", P[1, 1:-1]), ("t_hi", P[T, 1:-1]), ("z_lo", P[1:-1, 1]), ("z_hi", P[1:-1, Z]))}
+
+    def nb(key, dz, dt):
+        return every[key][((cz + dz) % pz) + pz * ((ct + dt) % pt)]
+
+    P[0, 1:-1] = nb("t_hi", 0, -1)
+    P[T + 1, 1:-1] = nb("t_lo", 0, +1)
+    P[1:-1, 0] = nb("z_hi", -1, 0)
+    P[1:-1, Z + 1] = nb("z_lo", +1, 0)
+    return P
+
+
 # ---- parity of the timed operator on the bench lattice ------------------------------------------------------------------
 def parity_check(torch, dist, cgpt, U, src, dst, dims, mpi, rank, n_sites4=9000):
     """
@@ -159,34 +183,26 @@ def parity_check(torch, dist, cgpt, U, src, dst, dims, mpi, rank, n_sites4=9000)
     cref.set_num_threads(max(1, cref.host_cores() // max(1, min(world, 8))))
     X, Y, Z, T = dims
     assert mpi[0] == 1 and mpi[1] == 1, "parity check: T and Z splits"
-    pz, pt = mpi[2], mpi[3]
-    cz, ct = rank % pz, rank // pz
 
     def padded(lat, ncomp):
         """local field in GPT order -> [T + 2, Z + 2, Y * X * ncomp] with the neighbours' faces"""
-        row = Y * X * ncomp
-        flat = np.empty(T * Z * row, dtype=np.complex64)
+        flat = np.empty(T * Z * Y * X * ncomp, dtype=np.complex64)
         cgpt.lattice_export_ptr(lat.obj, flat.ctypes.data, flat.nbytes)
-        P = np.zeros((T + 2, Z + 2, row), dtype=np.complex64)
-        P[1:-1, 1:-1] = flat.reshape(T, Z, row)
-        del flat
-        faces = {"t_lo": P[1, 1:-1], "t_hi": P[T, 1:-1], "z_lo": P[1:-1, 1], "z_hi": P[1:-1, Z]}
-        if world == 1:
-            got = {k: v.copy() for k, v in faces.items()}
-            nb = lambda key, dz, dt: got[key]  # noqa: E731
-        else:
-            every = {}
-            for k, v in faces.items():
-                mine = torch.from_numpy(np.ascontiguousarray(v)).cuda()
-                ev = torch.empty((world,) + tuple(mine.shape), dtype=mine.dtype, device="cuda")
-                dist.all_gather_into_tensor(ev, mine)
-                every[k] = ev
-            nb = lambda key, dz, dt: every[key][((cz + dz) % pz) + pz * ((ct + dt) % pt)].cpu().numpy()  # noqa: E731
-        P[0, 1:-1] = nb("t_hi", 0, -1)
-        P[T + 1, 1:-1] = nb("t_lo", 0, +1)
-        P[1:-1, 0] = nb("z_hi", -1, 0)
-        P[1:-1, Z + 1] = nb("z_lo", +1, 0)
-        return P
+
+        def gather(face):
+            if world == 1:
+                return [face]
+            mine = torch.from_numpy(np.ascontiguousarray(face)).cuda()
+            ev = torch.empty((world,) + tuple(mine.shape), dtype=mine.dtype, device="cuda")
+            dist.all_gather_into_tensor(ev, mine)
+
+            class _Faces:  # only the two neighbours' faces are copied to the host
+                def __getitem__(self, r):
+                    return ev[r].cpu().numpy()
+
+            return _Faces()
+
+        return pad_with_neighbour_faces(flat, dims, ncomp, mpi, rank, gather)
 
     psi = padded(src, LS * 12)
     V = np.stack([padded(U[mu], 9) for mu in range(4)])
